@@ -1,0 +1,133 @@
+"""Pins the oracle (oracle/fd1d_oracle.c) to the reference: bit-for-bit against the committed
+golden vectors (made by the unmodified reference, tests/golden/make_golden.py), against the
+live reference build when present, and against the reference's own test bars."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, synthetic_cases
+
+
+def test_kat_matches_reference_tests(oracle):
+    # test/kwPricer_test.cpp:63-84 (FD1D), :37-60 (BS), :87-108 (FD1D-BS): |want-got| <= 1.3e-3
+    g = load_golden("kat")
+    o, want = g["options"], g["want"]
+    p, err = oracle.fd1d(o, 512, 512)
+    assert err == ""
+    assert np.max(np.abs(p - want)) <= 1.3e-3
+    assert np.array_equal(p, g["fd1d_512"])
+    bs, _ = oracle.fd1d(o, mode="BS")
+    euro = o["e"] == 0
+    assert np.all(np.isnan(bs[~euro]))  # src/Pricer/kwBlackScholes.cpp:30-33
+    assert np.max(np.abs(bs[euro] - want[euro])) <= 1.3e-3
+    assert np.array_equal(bs, g["bs"], equal_nan=True)
+    fb, err = oracle.fd1d(o, 512, 512, mode="FD1D-BS")
+    assert err == ""
+    assert np.array_equal(fb, g["fd1d_bs_512"], equal_nan=True)
+    assert np.nanmax(np.abs(fb - want)) <= 1.3e-3
+    p, _ = oracle.fd1d(o, 1024, 1024)
+    assert np.array_equal(p, g["fd1d_1024"])
+
+
+def test_survey_recorded_values(oracle):
+    # reference outputs observed for the KATs at 512^2
+    g = load_golden("kat")
+    rec = [10.626938726208042, 5.8853370643656095, 2.9874136574651469, 4.668573598126291,
+           9.7290028085570839, 16.633092796918213, 13.988158670348433, 8.4093250376167035,
+           4.659405086670291, 2.9471231705371621, 6.841850924591987, 12.79306401532172]
+    p, _ = oracle.fd1d(g["options"], 512, 512)
+    assert np.array_equal(p, np.array(rec))
+
+
+@pytest.mark.parametrize("name", ["portfolio_fd1d", "portfolio_qdfp"])
+def test_fixture_bitexact_512(oracle, name):
+    g = load_golden(name)
+    p, err = oracle.fd1d(g["options"], 512, 512)
+    assert err == ""
+    assert np.array_equal(p, g["fd1d_512"])
+    if name == "portfolio_qdfp":
+        # test/kwPortfolio_test.cpp:29-58: |QuantLib - FD1D| <= 5e-3 on all 6000
+        assert np.max(np.abs(p - g["quantlib"])) <= 5e-3
+
+
+def test_fixture_bitexact_1024(oracle):
+    g = load_golden("portfolio_fd1d")
+    p, err = oracle.fd1d(g["options"], 1024, 1024)
+    assert err == ""
+    assert np.array_equal(p, g["fd1d_1024"])
+
+
+def test_fixture_chain_compression(oracle):
+    # 6000 options -> 600 chains (src/Pricer/kwFd1d.cpp:28-65); same prices without compression
+    g = load_golden("portfolio_fd1d")
+    o = g["options"][::7]
+    a, _ = oracle.fd1d(o, 128, 128, compress=True)
+    b, _ = oracle.fd1d(o, 128, 128, compress=False)
+    assert np.array_equal(a, b)
+
+
+def test_synthetic_bitexact(oracle):
+    g, keys = synthetic_cases()
+    for k in keys:
+        t, x = (int(v) for v in g[k + "/grid"])
+        if x >= 4096:
+            continue  # covered in test_synthetic_4096
+        d, s = g[k + "/params"]
+        p, err = oracle.fd1d(g[k + "/options"], t, x, density=float(d), scale=float(s))
+        assert err == "", k
+        assert np.array_equal(p, g[k + "/fd1d"]), k
+    p, _ = oracle.fd1d(g["bs_mix/options"], 512, 512, mode="FD1D-BS")
+    assert np.array_equal(p, g["bs_mix/fd1d_bs"], equal_nan=True)
+    p, _ = oracle.fd1d(g["bs_mix/options"], mode="BS")
+    assert np.array_equal(p, g["bs_mix/bs"], equal_nan=True)
+
+
+def test_synthetic_4096(oracle):
+    g, _ = synthetic_cases()
+    o = g["c5_4096/options"][:8]
+    p, err = oracle.fd1d(o, 4096, 4096)
+    assert err == ""
+    assert np.array_equal(p, g["c5_4096/fd1d"][:8])
+
+
+def test_live_reference_bitexact(oracle, reflib):
+    # the oracle against the reference itself (compiled here), on inputs not in the golden set
+    from kwfd1d.synthetic import synthetic_options
+
+    o = synthetic_options(64, 2024, european_every=3, call_every=2)
+    for t, x in ((200, 333), (512, 512)):
+        a, ea = oracle.fd1d(o, t, x)
+        b, eb = reflib.price(o, t, x)
+        assert ea == "" and eb == ""
+        assert np.array_equal(a, b)
+    a, _ = oracle.fd1d(o, 64, 64, mode="FD1D-BS")
+    b, _ = reflib.price(o, 64, 64, mode="FD1D-BS")
+    assert np.array_equal(a, b, equal_nan=True)
+
+
+def test_errors_and_edges(oracle, reflib=None):
+    from kwfd1d.types import make_options
+
+    # n == 0: success, nothing written (src/Pricer/kwFd1d.cpp:24-26)
+    p, err = oracle.fd1d(np.zeros(0, dtype=load_golden("kat")["options"].dtype))
+    assert err == "" and p.shape == (0,)
+    # log(s/k) outside the grid -> error for the whole call (src/Math/kwFd1d.cpp:151-153)
+    o = make_options([(1.0, 100., 0.2, 0.06, 0.02, 100., 1, -1), (1.0, 1e-9, 0.01, 0.06, 0.02, 100., 1, -1)])
+    p, err = oracle.fd1d(o, 64, 64)
+    assert "not in range" in err
+    # Thomas solver error codes (src/Math/kwMath.cpp:18-23)
+    x, rc = oracle.solve_tridiagonal([0, 1, 1], [0, 2, 2], [1, 1, 0], [1, 1, 1])
+    assert rc == 1
+    x, rc = oracle.solve_tridiagonal([0, 1], [2, 2], [1, 0], [1, 1])
+    assert rc == 3
+    x, rc = oracle.solve_tridiagonal([0, -1, -1, -1], [2, 2, 2, 2], [-1, -1, -1, 0], [1, 0, 0, 1])
+    assert rc == 0 and np.allclose(x, 1.0)
+
+
+def test_reference_error_matches(oracle, reflib):
+    from kwfd1d.types import make_options
+
+    o = make_options([(1.0, 1e-9, 0.01, 0.06, 0.02, 100., 1, -1)])
+    _, ea = oracle.fd1d(o, 64, 64)
+    _, eb = reflib.price(o, 64, 64)
+    assert ea != "" and eb != ""
+    assert eb.startswith("Fd1d_Pricer::price Fd1d::value: x=")
