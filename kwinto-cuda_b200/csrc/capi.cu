@@ -1,0 +1,625 @@
+// capi.cu -- the extern "C" layer of include/kw_fd1d.h: handle, device-resident asset/price
+// buffers, host-side chain compression, kernel dispatch.
+//
+// Reference functions replaced on this path:
+//   Fd1d_Pricer::init   src/Pricer/kwFd1d.cpp:9-19     -> kw_fd1d_create
+//   Fd1d_Pricer::price  src/Pricer/kwFd1d.cpp:21-160   -> kw_fd1d_price / kw_fd1d_price_device
+//   Fd1d_BlackScholes_Pricer::price src/Pricer/kwFd1d_BlackScholes.cpp:15-43 -> kw_fd1d_price_bs
+// There is NO CPU fallback here: without a CUDA device every entry point fails loudly.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "fd1d_common.cuh"
+#include "fd1d_reg.cuh"
+#include "fd1d_soa.cuh"
+#include "microbench.cuh"
+
+using namespace kwfd1d;
+
+namespace {
+
+// ---------------------------------------------------------------- variants of Layout B
+typedef void (*RegKernel)(const Fd1dBatch);
+struct RegVariant {
+    int id;        // 100*log2(P/32) + 10*MINB + DQ_SMEM
+    int M, P, minb;
+    bool dq_smem;
+    RegKernel fn;
+    size_t smem;
+};
+
+#define KW_VARIANT(LOG, M_, P_, MINB_, DQ_)                                                   \
+    {                                                                                          \
+        100 * (LOG) + 10 * (MINB_ > 9 ? 9 : MINB_) + (DQ_ ? 1 : 0), M_, P_, MINB_, DQ_,        \
+            fd1d_reg_kernel<M_, P_, MINB_, DQ_>, RegSmem<M_, P_>::bytes(DQ_)                   \
+    }
+
+const RegVariant g_variants[] = {
+    KW_VARIANT(0, 8, 32, 12, false),  // x <= 256
+    KW_VARIANT(0, 8, 32, 16, true),
+    KW_VARIANT(1, 8, 64, 6, false),   // x <= 512
+    KW_VARIANT(1, 8, 64, 8, true),
+    KW_VARIANT(1, 8, 64, 8, false),
+    KW_VARIANT(2, 8, 128, 3, false),  // x <= 1024
+    KW_VARIANT(2, 8, 128, 3, true),
+    KW_VARIANT(2, 8, 128, 4, true),
+    KW_VARIANT(2, 8, 128, 4, false),
+    KW_VARIANT(3, 8, 256, 1, false),  // x <= 2048
+    KW_VARIANT(3, 8, 256, 2, true),
+    KW_VARIANT(4, 8, 512, 1, true),   // x <= 4096
+    KW_VARIANT(4, 8, 512, 1, false),
+};
+constexpr int kNumVariants = sizeof(g_variants) / sizeof(g_variants[0]);
+constexpr int kMaxRegX = 4096;
+
+const RegVariant* find_variant(int xDim, int want_id)
+{
+    const RegVariant* first_fit = nullptr;
+    for (int i = 0; i < kNumVariants; ++i) {
+        const RegVariant& v = g_variants[i];
+        if (v.M * v.P < xDim) continue;
+        if (!first_fit || v.P < first_fit->P) first_fit = &v;
+    }
+    if (!first_fit) return nullptr;
+    if (want_id > 0) {
+        for (int i = 0; i < kNumVariants; ++i)
+            if (g_variants[i].id == want_id && g_variants[i].M * g_variants[i].P >= xDim) return &g_variants[i];
+        return nullptr;
+    }
+    // auto: the first entry of the smallest fitting P (the table lists the default first)
+    for (int i = 0; i < kNumVariants; ++i)
+        if (g_variants[i].P == first_fit->P) return &g_variants[i];
+    return first_fit;
+}
+
+__global__ void status_reset_kernel(unsigned int* status)
+{
+    status[0] = 0u;
+    status[1] = 0xffffffffu;
+}
+
+// BlackScholes_Pricer::priceOne (src/Pricer/kwBlackScholes.cpp:27-50) on European copies and
+// the control-variate combination of src/Pricer/kwFd1d_BlackScholes.cpp:38-40:
+//   prices[i] += bs[i] - fdEuro[i]
+__global__ void bs_combine_kernel(const kw_option* opts, size_t n, double* prices, const double* fd_euro)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const kw_option o = load_option(opts + i);
+    const double w = (double)o.w;
+    const double zt = __dmul_rn(o.z, sqrt(o.t));
+    const double drift = __dadd_rn(__dsub_rn(o.r, o.q), __dmul_rn(__dmul_rn(0.5, o.z), o.z));
+    const double d1 = __dmul_rn(1 / zt, __dadd_rn(log(o.s / o.k), __dmul_rn(drift, o.t)));
+    const double d2 = __dsub_rn(d1, zt);
+    const double isq2 = 1.4142135623730951;
+    const double n1 = 0.5 * (1 + erf(w * d1 / isq2));
+    const double n2 = 0.5 * (1 + erf(w * d2 / isq2));
+    const double bs = w * (__dsub_rn(__dmul_rn(__dmul_rn(o.s, n1), exp(-o.q * o.t)),
+                                     __dmul_rn(__dmul_rn(o.k, n2), exp(-o.r * o.t))));
+    prices[i] = __dadd_rn(prices[i], __dsub_rn(bs, fd_euro[i]));
+}
+
+struct KeyHash {
+    size_t operator()(const kw_option& o) const
+    {
+        auto mix = [](uint64_t h, uint64_t v) {
+            h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+            return h;
+        };
+        uint64_t b[4];
+        memcpy(&b[0], &o.t, 8);
+        memcpy(&b[1], &o.r, 8);
+        memcpy(&b[2], &o.q, 8);
+        memcpy(&b[3], &o.z, 8);
+        uint64_t h = 0x243f6a8885a308d3ull;
+        for (int i = 0; i < 4; ++i) h = mix(h, b[i] * 0xff51afd7ed558ccdull);
+        h = mix(h, ((uint64_t)o.e << 8) | (uint8_t)o.w);
+        return (size_t)h;
+    }
+};
+struct KeyEq {
+    // the reference's chain key (src/Pricer/kwFd1d.cpp:33-35): (t, r, q, z, e, w); s, k are not in it
+    bool operator()(const kw_option& l, const kw_option& r) const
+    {
+        return l.t == r.t && l.r == r.r && l.q == r.q && l.z == r.z && l.e == r.e && l.w == r.w;
+    }
+};
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = n + n / 4 + 64;
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+template <class T>
+struct PinBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = n + n / 4 + 64;
+        cudaError_t e = cudaMallocHost(&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace
+
+struct kw_fd1d_handle {
+    kw_fd1d_config cfg;
+    std::string err;
+    int sm_count = 0;
+    int clock_khz = 0;
+    char name[128] = {0};
+
+    int layout = 0;
+    const RegVariant* var = nullptr;
+    int ctas_per_sm = 0;
+    int regs = 0;
+    int last_grid = 0;
+    uint64_t last_n_pde = 0;
+
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_valid = false;
+
+    DevBuf<kw_option> d_opts, d_opts2;
+    DevBuf<double> d_prices, d_prices2;
+    DevBuf<uint32_t> d_rep, d_start, d_csr;
+    DevBuf<unsigned int> d_status;
+    DevBuf<double> d_soa;
+    PinBuf<uint32_t> h_idx;  // rep | start | csr staging
+    PinBuf<unsigned int> h_status;
+};
+
+namespace {
+
+int fail(kw_fd1d_handle* h, int code, const std::string& msg)
+{
+    if (h) h->err = msg;
+    return code;
+}
+
+#define KW_CUDA(h, call)                                                                       \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(h, KW_FD1D_ECUDA,                                                      \
+                        std::string("Fd1dGpu_Pricer: CUDA error: ") + cudaGetErrorString(e_) + \
+                            " at " #call);                                                     \
+    } while (0)
+
+size_t soa_chunk(const kw_fd1d_handle* h, size_t n_pde)
+{
+    (void)h;
+    return std::min<size_t>(n_pde, 65536);
+}
+
+// enqueue the solve of `n_pde` PDEs on `st`; all pointers are device pointers
+int launch_batch(kw_fd1d_handle* h, Fd1dBatch B, cudaStream_t st)
+{
+    status_reset_kernel<<<1, 1, 0, st>>>(B.status);
+    h->last_n_pde = B.n_pde;
+    if (h->layout == KW_FD1D_LAYOUT_REG) {
+        const RegVariant* v = h->var;
+        int grid = h->sm_count * h->ctas_per_sm;
+        if ((uint32_t)grid > B.n_pde) grid = (int)B.n_pde;
+        h->last_grid = grid;
+        KW_CUDA(h, cudaEventRecord(h->ev0, st));
+        v->fn<<<grid, v->P, v->smem, st>>>(B);
+        KW_CUDA(h, cudaEventRecord(h->ev1, st));
+        h->ev_valid = true;
+        KW_CUDA(h, cudaGetLastError());
+        return KW_FD1D_OK;
+    }
+    // Layout A: chunks of PDEs, 7 SoA arrays each
+    const size_t chunk = soa_chunk(h, B.n_pde);
+    const size_t per = (size_t)B.xDim * chunk;
+    KW_CUDA(h, h->d_soa.reserve(7 * per));
+    KW_CUDA(h, cudaEventRecord(h->ev0, st));
+    for (size_t base = 0; base < B.n_pde; base += chunk) {
+        const uint32_t cnt = (uint32_t)std::min<size_t>(chunk, B.n_pde - base);
+        SoaWork W;
+        const size_t pitch = (size_t)B.xDim * cnt;
+        W.A = h->d_soa.p;
+        W.G = W.A + pitch;
+        W.D = W.G + pitch;
+        W.PR = W.D + pitch;
+        W.V = W.PR + pitch;
+        W.Y = W.V + pitch;
+        W.X = W.Y + pitch;
+        W.n = cnt;
+        Fd1dBatch Bc = B;
+        Bc.pde_base = (uint32_t)base;
+        const int tpb = 128;
+        const int grid = (int)((cnt + tpb - 1) / tpb);
+        h->last_grid = grid;
+        fd1d_soa_setup_kernel<<<grid, tpb, 0, st>>>(Bc, W);
+        fd1d_soa_march_kernel<<<grid, tpb, 0, st>>>(Bc, W);
+        fd1d_soa_value_kernel<<<grid, tpb, 0, st>>>(Bc, W);
+    }
+    KW_CUDA(h, cudaEventRecord(h->ev1, st));
+    h->ev_valid = true;
+    KW_CUDA(h, cudaGetLastError());
+    return KW_FD1D_OK;
+}
+
+// host mirror of the reference's error text (src/Math/kwFd1d.cpp:151-153 via
+// src/Pricer/kwFd1d.cpp:154-155)
+std::string range_message(const kw_fd1d_handle* h, const kw_option& o)
+{
+    const double x_ = std::log(o.s / o.k);
+    const double half = h->cfg.scale * o.z * std::sqrt(o.t);
+    const double x0 = h->cfg.density * std::sinh(std::asinh((0. - half) / h->cfg.density));
+    const double x1 = h->cfg.density * std::sinh(std::asinh((0. + half) / h->cfg.density));
+    return "Fd1d_Pricer::price Fd1d::value: x=" + std::to_string(x_) + " not in range (" +
+           std::to_string(x0) + ", " + std::to_string(x1) + ")";
+}
+
+// Chain compression (src/Pricer/kwFd1d.cpp:28-65): rep[m], start[m+1], csr[n] into pinned staging.
+// A hash on the key replaces the reference's sort; PDE numbering differs, prices do not.
+int compress(kw_fd1d_handle* h, const kw_option* a, size_t n, size_t& m, uint32_t*& rep, uint32_t*& start,
+             uint32_t*& csr)
+{
+    KW_CUDA(h, h->h_idx.reserve(3 * n + 2));
+    rep = h->h_idx.p;
+    start = rep + n;
+    csr = start + n + 1;
+    std::vector<uint32_t> a2p(n);
+    std::unordered_map<kw_option, uint32_t, KeyHash, KeyEq> map;
+    map.reserve(n * 2);
+    m = 0;
+    for (size_t i = 0; i < n; ++i) {
+        auto it = map.find(a[i]);
+        if (it == map.end()) {
+            map.emplace(a[i], (uint32_t)m);
+            rep[m] = (uint32_t)i;
+            a2p[i] = (uint32_t)m;
+            ++m;
+        } else {
+            a2p[i] = it->second;
+        }
+    }
+    std::fill(start, start + m + 1, 0u);
+    for (size_t i = 0; i < n; ++i) start[a2p[i] + 1]++;
+    for (size_t p = 0; p < m; ++p) start[p + 1] += start[p];
+    std::vector<uint32_t> fillp(start, start + m);
+    for (size_t i = 0; i < n; ++i) csr[fillp[a2p[i]]++] = (uint32_t)i;
+    return KW_FD1D_OK;
+}
+
+// host assets -> device prices in `d_out` (n doubles) on the handle's stream; no final sync
+int price_to_device(kw_fd1d_handle* h, const kw_option* assets, size_t n, DevBuf<kw_option>& d_opts,
+                    double* d_out)
+{
+    KW_CUDA(h, d_opts.reserve(n));
+    KW_CUDA(h, h->d_status.reserve(2));
+    KW_CUDA(h, cudaMemcpyAsync(d_opts.p, assets, n * sizeof(kw_option), cudaMemcpyHostToDevice, h->stream));
+    Fd1dBatch B;
+    memset(&B, 0, sizeof B);
+    B.opts = d_opts.p;
+    B.prices = d_out;
+    B.status = h->d_status.p;
+    B.tDim = (int32_t)h->cfg.t_grid_size;
+    B.xDim = (int32_t)h->cfg.x_grid_size;
+    B.density = h->cfg.density;
+    B.scale = h->cfg.scale;
+    if (h->cfg.compress) {
+        size_t m;
+        uint32_t *rep, *start, *csr;
+        if (int rc = compress(h, assets, n, m, rep, start, csr)) return rc;
+        if (m < n) {
+            KW_CUDA(h, h->d_rep.reserve(m));
+            KW_CUDA(h, h->d_start.reserve(m + 1));
+            KW_CUDA(h, h->d_csr.reserve(n));
+            KW_CUDA(h, cudaMemcpyAsync(h->d_rep.p, rep, m * 4, cudaMemcpyHostToDevice, h->stream));
+            KW_CUDA(h, cudaMemcpyAsync(h->d_start.p, start, (m + 1) * 4, cudaMemcpyHostToDevice, h->stream));
+            KW_CUDA(h, cudaMemcpyAsync(h->d_csr.p, csr, n * 4, cudaMemcpyHostToDevice, h->stream));
+            B.pde_rep = h->d_rep.p;
+            B.csr_start = h->d_start.p;
+            B.csr_opt = h->d_csr.p;
+        }
+        B.n_pde = (uint32_t)m;
+    } else {
+        B.n_pde = (uint32_t)n;
+    }
+    return launch_batch(h, B, h->stream);
+}
+
+int check_status(kw_fd1d_handle* h, cudaStream_t st, const kw_option* host_assets)
+{
+    KW_CUDA(h, h->h_status.reserve(2));
+    KW_CUDA(h, cudaMemcpyAsync(h->h_status.p, h->d_status.p, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    KW_CUDA(h, cudaStreamSynchronize(st));
+    if (h->h_status.p[0] != 0) {
+        const unsigned int idx = h->h_status.p[1];
+        if (host_assets) return fail(h, KW_FD1D_ERANGE, range_message(h, host_assets[idx]));
+        return fail(h, KW_FD1D_ERANGE,
+                    "Fd1d_Pricer::price Fd1d::value: x not in range (option " + std::to_string(idx) + ")");
+    }
+    return KW_FD1D_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void kw_fd1d_config_default(kw_fd1d_config* cfg)
+{
+    memset(cfg, 0, sizeof *cfg);
+    cfg->density = 0.25;  // src/Pricer/kwFd1d.cpp:12
+    cfg->scale = 50.;     // :13
+    cfg->t_grid_size = 512;
+    cfg->x_grid_size = 512;
+    cfg->device = 0;
+    cfg->precision = KW_FD1D_F64;
+    cfg->layout = KW_FD1D_LAYOUT_AUTO;
+    cfg->compress = 1;
+    cfg->variant = 0;
+}
+
+int kw_fd1d_create(const kw_fd1d_config* cfg, kw_fd1d_handle** out)
+{
+    if (!cfg || !out) return KW_FD1D_EINVAL;
+    *out = nullptr;
+    kw_fd1d_handle* h = new kw_fd1d_handle();
+    h->cfg = *cfg;
+    *out = h;  // returned even on failure so the caller can read the message; destroy it either way
+    if (cfg->t_grid_size < 2 || cfg->x_grid_size < 3 || cfg->t_grid_size > (1 << 24) || cfg->x_grid_size > (1 << 20))
+        return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::init: FD1D.T_GRID_SIZE must be >= 2 and FD1D.X_GRID_SIZE >= 3");
+    if (!(cfg->density > 0) || !(cfg->scale > 0))
+        return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::init: FD1D.DENSITY and FD1D.SCALE must be positive");
+    if (cfg->precision != KW_FD1D_F64)
+        return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::init: only FD1D.GPU.PRECISION = f64 is built in this round");
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(h, KW_FD1D_ECUDA,
+                    std::string("Fd1dGpu_Pricer::init: no CUDA device (") + cudaGetErrorString(e) +
+                        "); this pricer has no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= ndev)
+        return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::init: FD1D.GPU.DEVICE out of range");
+    KW_CUDA(h, cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    KW_CUDA(h, cudaGetDeviceProperties(&prop, cfg->device));
+    h->sm_count = prop.multiProcessorCount;
+    strncpy(h->name, prop.name, sizeof h->name - 1);
+    KW_CUDA(h, cudaDeviceGetAttribute(&h->clock_khz, cudaDevAttrClockRate, cfg->device));
+    if (prop.major < 10)
+        return fail(h, KW_FD1D_ECUDA, "Fd1dGpu_Pricer::init: kernels are built for sm_100a only; found " + std::string(prop.name));
+
+    // layout resolution (DESIGN.md "dispatch"): register layout wherever a tile fits
+    int layout = cfg->layout;
+    if (layout == KW_FD1D_LAYOUT_AUTO) layout = cfg->x_grid_size <= kMaxRegX ? KW_FD1D_LAYOUT_REG : KW_FD1D_LAYOUT_SOA;
+    if (layout == KW_FD1D_LAYOUT_REG) {
+        h->var = find_variant((int)cfg->x_grid_size, cfg->variant);
+        if (!h->var)
+            return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::init: no register-layout kernel variant for this FD1D.X_GRID_SIZE / FD1D.GPU.VARIANT");
+        KW_CUDA(h, cudaFuncSetAttribute(h->var->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->var->smem));
+        cudaFuncAttributes fa;
+        KW_CUDA(h, cudaFuncGetAttributes(&fa, h->var->fn));
+        h->regs = fa.numRegs;
+        int occ = 0;
+        KW_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->var->fn, h->var->P, h->var->smem));
+        if (occ < 1) return fail(h, KW_FD1D_ECUDA, "Fd1dGpu_Pricer::init: kernel variant does not fit on an SM");
+        h->ctas_per_sm = occ;
+    } else if (layout == KW_FD1D_LAYOUT_SOA) {
+        cudaFuncAttributes fa;
+        KW_CUDA(h, cudaFuncGetAttributes(&fa, fd1d_soa_march_kernel));
+        h->regs = fa.numRegs;
+        h->ctas_per_sm = 0;
+    } else {
+        return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::init: unknown FD1D.GPU.LAYOUT");
+    }
+    h->layout = layout;
+    KW_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    KW_CUDA(h, cudaEventCreate(&h->ev0));
+    KW_CUDA(h, cudaEventCreate(&h->ev1));
+    KW_CUDA(h, h->d_status.reserve(2));
+    KW_CUDA(h, h->h_status.reserve(2));
+    return KW_FD1D_OK;
+}
+
+void kw_fd1d_destroy(kw_fd1d_handle* h)
+{
+    if (!h) return;
+    if (h->stream) {
+        cudaSetDevice(h->cfg.device);
+        cudaStreamSynchronize(h->stream);
+    }
+    h->d_opts.release();
+    h->d_opts2.release();
+    h->d_prices.release();
+    h->d_prices2.release();
+    h->d_rep.release();
+    h->d_start.release();
+    h->d_csr.release();
+    h->d_status.release();
+    h->d_soa.release();
+    h->h_idx.release();
+    h->h_status.release();
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int kw_fd1d_price(kw_fd1d_handle* h, const kw_option* assets, size_t n, double* prices)
+{
+    if (!h) return KW_FD1D_EINVAL;
+    if (!h->stream) return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::price: pricer was not initialised");
+    h->err.clear();
+    if (n == 0) return KW_FD1D_OK;  // src/Pricer/kwFd1d.cpp:24-26
+    if (!assets || !prices) return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::price: null buffer");
+    if (n > 0xfffffff0ull) return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::price: batch too large");
+    KW_CUDA(h, cudaSetDevice(h->cfg.device));
+    KW_CUDA(h, h->d_prices.reserve(n));
+    if (int rc = price_to_device(h, assets, n, h->d_opts, h->d_prices.p)) return rc;
+    KW_CUDA(h, cudaMemcpyAsync(prices, h->d_prices.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    return check_status(h, h->stream, assets);
+}
+
+int kw_fd1d_price_bs(kw_fd1d_handle* h, const kw_option* assets, size_t n, double* prices)
+{
+    if (!h) return KW_FD1D_EINVAL;
+    if (!h->stream) return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::price: pricer was not initialised");
+    h->err.clear();
+    if (n == 0) return KW_FD1D_OK;
+    if (!assets || !prices) return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::price: null buffer");
+    KW_CUDA(h, cudaSetDevice(h->cfg.device));
+    KW_CUDA(h, h->d_prices.reserve(n));
+    KW_CUDA(h, h->d_prices2.reserve(n));
+    // 1. FD as given (src/Pricer/kwFd1d_BlackScholes.cpp:18)
+    if (int rc = price_to_device(h, assets, n, h->d_opts, h->d_prices.p)) return rc;
+    if (int rc = check_status(h, h->stream, assets)) return rc;
+    // 2. FD on European copies (:21-28)
+    std::vector<kw_option> euro(assets, assets + n);
+    for (auto& o : euro) o.e = 0;
+    if (int rc = price_to_device(h, euro.data(), n, h->d_opts2, h->d_prices2.p)) return rc;
+    // 3. + (BS - FD_euro) (:30-40)
+    bs_combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_opts2.p, n, h->d_prices.p, h->d_prices2.p);
+    KW_CUDA(h, cudaGetLastError());
+    KW_CUDA(h, cudaMemcpyAsync(prices, h->d_prices.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    return check_status(h, h->stream, euro.data());
+}
+
+int kw_fd1d_price_device(kw_fd1d_handle* h, const kw_option* d_assets, size_t n, double* d_prices, void* stream)
+{
+    if (!h) return KW_FD1D_EINVAL;
+    if (!h->stream) return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::price: pricer was not initialised");
+    h->err.clear();
+    if (n == 0) return KW_FD1D_OK;
+    if (!d_assets || !d_prices) return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::price: null buffer");
+    KW_CUDA(h, cudaSetDevice(h->cfg.device));
+    Fd1dBatch B;
+    memset(&B, 0, sizeof B);
+    B.opts = d_assets;
+    B.prices = d_prices;
+    B.status = h->d_status.p;
+    B.n_pde = (uint32_t)n;
+    B.tDim = (int32_t)h->cfg.t_grid_size;
+    B.xDim = (int32_t)h->cfg.x_grid_size;
+    B.density = h->cfg.density;
+    B.scale = h->cfg.scale;
+    return launch_batch(h, B, (cudaStream_t)stream);
+}
+
+int kw_fd1d_sync(kw_fd1d_handle* h, void* stream)
+{
+    if (!h) return KW_FD1D_EINVAL;
+    if (!h->stream) return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer: pricer was not initialised");
+    KW_CUDA(h, cudaSetDevice(h->cfg.device));
+    return check_status(h, (cudaStream_t)stream, nullptr);
+}
+
+const char* kw_fd1d_last_error(const kw_fd1d_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int kw_fd1d_get_info(const kw_fd1d_handle* hc, kw_fd1d_info* info)
+{
+    if (!hc || !info) return KW_FD1D_EINVAL;
+    kw_fd1d_handle* h = const_cast<kw_fd1d_handle*>(hc);
+    memset(info, 0, sizeof *info);
+    info->device = h->cfg.device;
+    info->sm_count = h->sm_count;
+    info->layout = h->layout;
+    info->variant = h->var ? h->var->id : 0;
+    info->threads_per_pde = h->var ? h->var->P : 1;
+    info->nodes_per_thread = h->var ? h->var->M : (int)h->cfg.x_grid_size;
+    info->ctas_per_sm = h->ctas_per_sm;
+    info->regs_per_thread = h->regs;
+    info->smem_per_cta = h->var ? (int)h->var->smem : 0;
+    info->grid = h->last_grid;
+    info->sm_clock_khz = h->clock_khz;
+    info->last_n_pde = h->last_n_pde;
+    info->last_kernel_ms = 0.;
+    if (h->ev_valid && cudaEventSynchronize(h->ev1) == cudaSuccess) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) info->last_kernel_ms = ms;
+    }
+    strncpy(info->device_name, h->name, sizeof info->device_name - 1);
+    return KW_FD1D_OK;
+}
+
+int kw_fd1d_fp64_peak(int32_t device, double* tflops, double* sm_mhz_effective)
+{
+    if (!tflops) return KW_FD1D_EINVAL;
+    if (cudaSetDevice(device) != cudaSuccess) return KW_FD1D_ECUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return KW_FD1D_ECUDA;
+    double* d = nullptr;
+    if (cudaMalloc(&d, 64) != cudaSuccess) return KW_FD1D_ECUDA;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int grid = prop.multiProcessorCount * 2, tpb = 1024, iters = 4096;
+    dfma_throughput_kernel<<<grid, tpb>>>(d, 64, 1.0);  // warm-up
+    double best = 0.;
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(e0);
+        dfma_throughput_kernel<<<grid, tpb>>>(d, iters, 1.0);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flop = 2.0 * 64.0 * (double)iters * (double)grid * tpb;
+        best = std::max(best, flop / (ms * 1e-3) * 1e-12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    if (cudaGetLastError() != cudaSuccess || best == 0.) return KW_FD1D_ECUDA;
+    *tflops = best;
+    if (sm_mhz_effective) *sm_mhz_effective = best * 1e12 / (2.0 * 64.0 * prop.multiProcessorCount) * 1e-6;
+    return KW_FD1D_OK;
+}
+
+int kw_fd1d_microbench(int32_t device, double* out8)
+{
+    if (!out8) return KW_FD1D_EINVAL;
+    if (cudaSetDevice(device) != cudaSuccess) return KW_FD1D_ECUDA;
+    double* d = nullptr;
+    if (cudaMalloc(&d, 8 * sizeof(double)) != cudaSuccess) return KW_FD1D_ECUDA;
+    cudaMemset(d, 0, 8 * sizeof(double));
+    latency_kernel<<<1, 128>>>(d, 1.0, 8);
+    latency_kernel<<<1, 128>>>(d, 1.0, 256);
+    cudaError_t e = cudaMemcpy(out8, d, 8 * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    return e == cudaSuccess ? KW_FD1D_OK : KW_FD1D_ECUDA;
+}
+
+const char* kw_fd1d_version(void) { return "kwinto-b200 fd1d 0.1 (sm_100a)"; }
+
+}  // extern "C"

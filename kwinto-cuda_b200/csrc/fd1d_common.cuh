@@ -1,0 +1,162 @@
+// fd1d_common.cuh -- shared device helpers of the Fd1d kernels (sm_100a).
+//
+// The scheme is the reference's (src/Math/kwFd1d.cpp:61-136): theta = 1/2 Crank-Nicolson,
+// B = 1 - dt/2 A assembled on the non-uniform sinh grid with one-sided, diffusion-free
+// boundary rows, Thomas solve, explicit projection v = max(v, payoff) on nodes 0..xDim-2.
+//
+// What is hoisted (DESIGN.md "Algebra"): dt is constant (t/(tDim-1)), so B and its LU are
+// time-invariant and C = 2I - B, hence one step is  v <- max(2 B^-1 v - v, payoff).
+// With beta_j the Thomas pivots and pivot-scaled unknowns y~ = beta*y, u~ = beta*u:
+//     y~_j = v_j + a~_j y~_{j-1},   a~_j = -bl_j / beta_{j-1}
+//     u~_j = y~_j + g~_j u~_{j+1},  g~_j = -bu_j / beta_{j+1}
+//     v'_j = max(D_j u~_j - v_j, p_j),   D_j = 2 / beta_j
+// i.e. 4 FP64-pipe instructions per node-step serial (3 FMA + 1 max), no division.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "../../include/kw_fd1d.h"
+
+namespace kwfd1d {
+
+// One batch of PDEs as the kernels see it.  With chain compression several options share
+// a PDE (reference src/Pricer/kwFd1d.cpp:28-65): pde_rep[p] is the option whose (t,r,q,z,e,w)
+// define PDE p and csr_start/csr_opt list the options priced from it.  All three null =
+// identity (PDE p == option p).
+struct Fd1dBatch {
+    const kw_option* opts;
+    const uint32_t* pde_rep;
+    const uint32_t* csr_start;
+    const uint32_t* csr_opt;
+    double* prices;
+    unsigned int* status;  // [0] = number of out-of-range options, [1] = smallest such index
+    uint32_t n_pde;
+    uint32_t pde_base;     // first PDE of this launch (layout A chunks the batch)
+    int32_t tDim;
+    int32_t xDim;
+    double density;
+    double scale;
+};
+
+struct PdeScalars {
+    double a0, ax, axx;  // src/Pricer/kwFd1d.cpp:80-83
+    double hdt;          // theta*dt with theta = 0.5 (src/Math/kwFd1d.h:31)
+    double yMin, yMax, dy;
+    bool american, put;
+};
+
+__device__ __forceinline__ kw_option load_option(const kw_option* p)
+{
+    // 56-byte struct, 8-byte aligned: seven 64-bit loads through the read-only path
+    const unsigned long long* q = reinterpret_cast<const unsigned long long*>(p);
+    kw_option o;
+    o.t = __longlong_as_double(__ldg(q + 0));
+    o.k = __longlong_as_double(__ldg(q + 1));
+    o.z = __longlong_as_double(__ldg(q + 2));
+    o.r = __longlong_as_double(__ldg(q + 3));
+    o.q = __longlong_as_double(__ldg(q + 4));
+    o.s = __longlong_as_double(__ldg(q + 5));
+    const unsigned long long ew = __ldg(q + 6);
+    o.e = (uint8_t)(ew & 0xff);
+    o.w = (int8_t)((ew >> 8) & 0xff);
+    return o;
+}
+
+// src/Pricer/kwFd1d.cpp:68-86 (coefficients), :95-99 (dt), :105-119 (y range).  The
+// _rn intrinsics keep the reference's evaluation order free of FMA contraction.
+__device__ __forceinline__ PdeScalars pde_scalars(const kw_option& o, const Fd1dBatch& B)
+{
+    PdeScalars s;
+    const double zz = __dmul_rn(o.z, o.z);
+    s.a0 = -o.r;
+    s.ax = __dsub_rn(__dsub_rn(o.r, o.q), zz / 2);
+    s.axx = zz / 2;
+    const double dt = o.t / (double)(B.tDim - 1);
+    s.hdt = 0.5 * dt;
+    const double half = __dmul_rn(__dmul_rn(B.scale, o.z), sqrt(o.t));
+    s.yMin = asinh((0. - half) / B.density);
+    s.yMax = asinh((0. + half) / B.density);
+    s.dy = 1. / (double)(B.xDim - 1);
+    s.american = o.e != 0;
+    s.put = o.w < 0;
+    return s;
+}
+
+// x_j, src/Pricer/kwFd1d.cpp:120-124
+__device__ __forceinline__ double x_node(const PdeScalars& s, double density, int j)
+{
+    const double yj = __dmul_rn((double)j, s.dy);
+    const double arg = __dadd_rn(__dmul_rn(s.yMin, 1.0 - yj), __dmul_rn(s.yMax, yj));
+    return __dmul_rn(density, sinh(arg));
+}
+
+// payoff in strike units, src/Pricer/kwFd1d.cpp:127-139
+__device__ __forceinline__ double payoff_node(bool put, double x)
+{
+    const double ex = exp(x);
+    const double p = put ? (1. - ex) : (ex - 1.);
+    return 0 < p ? p : 0.;
+}
+
+// Row j of B = 1 - theta*dt*A, src/Math/kwFd1d.cpp:73-114, with the constant dt.
+// xm, x0, xp = x_{j-1}, x_j, x_{j+1} (unused neighbours may be anything).
+__device__ __forceinline__ void b_row(const PdeScalars& s, int j, int xDim, double xm, double x0,
+                                      double xp, double& bl, double& b, double& bu)
+{
+    const double hdt = s.hdt, a0 = s.a0, ax = s.ax, axx = s.axx;
+    if (j >= xDim) {  // padding rows: identity, decoupled
+        bl = 0.;
+        b = 1.;
+        bu = 0.;
+    } else if (j == 0) {
+        const double inv_dx = 1. / (xp - x0);
+        bl = 0.;
+        b = __dsub_rn(1., __dmul_rn(hdt, __dsub_rn(a0, __dmul_rn(inv_dx, ax))));
+        bu = -__dmul_rn(hdt, __dmul_rn(inv_dx, ax));
+    } else if (j == xDim - 1) {
+        const double inv_dx = 1. / (x0 - xm);
+        bl = -__dmul_rn(hdt, __dmul_rn(-inv_dx, ax));
+        b = __dsub_rn(1., __dmul_rn(hdt, __dadd_rn(a0, __dmul_rn(inv_dx, ax))));
+        bu = 0.;
+    } else {
+        const double inv_dxu = 1. / (xp - x0);
+        const double inv_dxm = 1. / (xp - xm);
+        const double inv_dxd = 1. / (x0 - xm);
+        const double inv_dx2u = __dmul_rn(__dmul_rn(2., inv_dxu), inv_dxm);
+        const double inv_dx2m = __dmul_rn(__dmul_rn(2., inv_dxd), inv_dxu);
+        const double inv_dx2l = __dmul_rn(__dmul_rn(2., inv_dxd), inv_dxm);
+        bl = -__dmul_rn(hdt, __dadd_rn(__dmul_rn(-inv_dxm, ax), __dmul_rn(inv_dx2l, axx)));
+        b = __dsub_rn(1., __dmul_rn(hdt, __dsub_rn(a0, __dmul_rn(inv_dx2m, axx))));
+        bu = -__dmul_rn(hdt, __dadd_rn(__dmul_rn(inv_dxm, ax), __dmul_rn(inv_dx2u, axx)));
+    }
+}
+
+// Fd1d::value, src/Math/kwFd1d.cpp:139-158 (+ the k multiplication of
+// src/Pricer/kwFd1d.cpp:156).  x is increasing, so the reference's linear search for the first
+// x[xi] >= x_ is a lower_bound.  XS / VS are callables j -> x_j / v_j.
+template <class XS, class VS>
+__device__ __forceinline__ void price_option(const Fd1dBatch& B, uint32_t oi, XS xs, VS vs)
+{
+    const kw_option o = load_option(B.opts + oi);
+    const double xq = log(o.s / o.k);
+    int lo = 0, hi = B.xDim;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (xs(mid) < xq)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    if (lo == 0 || lo == B.xDim) {
+        B.prices[oi] = CUDART_NAN;
+        atomicAdd(&B.status[0], 1u);
+        atomicMin(&B.status[1], oi);
+        return;
+    }
+    const double x1 = xs(lo), x0 = xs(lo - 1);
+    const double num = __dadd_rn(__dmul_rn(x1 - xq, vs(lo - 1)), __dmul_rn(xq - x0, vs(lo)));
+    B.prices[oi] = __dmul_rn(o.k, num / (x1 - x0));
+}
+
+}  // namespace kwfd1d
