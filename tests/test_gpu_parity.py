@@ -216,3 +216,18 @@ def test_baseline_size_config2_sample_and_properties(oracle):
     # idempotence / determinism at full size
     _, again = p.price(o)
     assert np.array_equal(again, got)
+
+
+def test_cpp_pricer_interface():
+    """The reference's own pricer tests (test/kwPricer_test.cpp:63-108) through the C++ kw::Pricer
+    subclass (kwinto-cuda_b200/host/kw/kwFd1dGpu.h), compiled by __graft_entry__.build()."""
+    import os
+    import subprocess
+
+    from conftest import ROOT
+
+    exe = os.path.join(ROOT, "kwinto-cuda_b200", "bin", "test_pricer")
+    assert os.path.exists(exe), "run __graft_entry__.build() first"
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "PASSED" in r.stdout
