@@ -325,6 +325,7 @@ def main():
                        "threads_per_pde": info["threads_per_pde"], "ctas_per_sm": info["ctas_per_sm"],
                        "regs_per_thread": info["regs_per_thread"], "smem_per_cta": info["smem_per_cta"],
                        "grid": info["grid"], "device": info["device_name"],
+                       "carry_mode_histogram": info["mode_count"],
                        "l2": "256 MiB device buffer zeroed before every step (inside the timed region)",
                        "parallelism": f"dp{world} (options sharded, no data-path collective)"},
             "roofline": roofline,

@@ -75,7 +75,10 @@ typedef struct kw_fd1d_config {
     int32_t compress;    /* 1 (default): one PDE per (t,r,q,z,e,w) chain, as the reference's */
                          /* compression (src/Pricer/kwFd1d.cpp:28-65); 0: one PDE per option */
     int32_t variant;     /* 0 = auto; otherwise a kernel variant id for tuning   */
-    int32_t reserved[3];
+    int32_t exact;       /* FD1D.GPU.EXACT: 0 (default) carry terms proven < 2^-56 may be    */
+                         /* dropped (DESIGN.md "Truncation"); 1: keep all scan levels;       */
+                         /* 2: keep every carry term                                         */
+    int32_t reserved[2];
 } kw_fd1d_config;
 
 typedef struct kw_fd1d_handle kw_fd1d_handle;
@@ -96,6 +99,7 @@ typedef struct kw_fd1d_info {
     int32_t reserved;
     double last_kernel_ms;    /* device time of the last batch's march launch(es), CUDA events */
     uint64_t last_n_pde;      /* PDEs solved by the last price call                          */
+    uint32_t mode_count[6];   /* layout B: PDEs of the last SYNCHRONISED call per carry mode 0..4 */
     char device_name[128];
 } kw_fd1d_info;
 

@@ -26,33 +26,35 @@ namespace {
 // ---------------------------------------------------------------- variants of Layout B
 typedef void (*RegKernel)(const Fd1dBatch);
 struct RegVariant {
-    int id;        // 100*log2(P/32) + 10*MINB + DQ_SMEM
+    int id;        // 100*log2(P/32) + serial; see the table
     int M, P, minb;
-    bool dq_smem;
+    bool proj_smem, dq_smem;
     RegKernel fn;
     size_t smem;
 };
 
-#define KW_VARIANT(LOG, M_, P_, MINB_, DQ_)                                                   \
-    {                                                                                          \
-        100 * (LOG) + 10 * (MINB_ > 9 ? 9 : MINB_) + (DQ_ ? 1 : 0), M_, P_, MINB_, DQ_,        \
-            fd1d_reg_kernel<M_, P_, MINB_, DQ_>, RegSmem<M_, P_>::bytes(DQ_)                   \
+#define KW_VARIANT(ID, M_, P_, MINB_, PJ_, DQ_)                                                   \
+    {                                                                                              \
+        ID, M_, P_, MINB_, PJ_, DQ_, fd1d_reg_kernel<M_, P_, MINB_, PJ_, DQ_>,                     \
+            RegSmem<M_, P_>::bytes(PJ_, DQ_)                                                       \
     }
 
+// the first entry of each P is the default of the per-xDim dispatch
 const RegVariant g_variants[] = {
-    KW_VARIANT(0, 8, 32, 12, false),  // x <= 256
-    KW_VARIANT(0, 8, 32, 16, true),
-    KW_VARIANT(1, 8, 64, 6, false),   // x <= 512
-    KW_VARIANT(1, 8, 64, 8, true),
-    KW_VARIANT(1, 8, 64, 8, false),
-    KW_VARIANT(2, 8, 128, 3, false),  // x <= 1024
-    KW_VARIANT(2, 8, 128, 3, true),
-    KW_VARIANT(2, 8, 128, 4, true),
-    KW_VARIANT(2, 8, 128, 4, false),
-    KW_VARIANT(3, 8, 256, 1, false),  // x <= 2048
-    KW_VARIANT(3, 8, 256, 2, true),
-    KW_VARIANT(4, 8, 512, 1, true),   // x <= 4096
-    KW_VARIANT(4, 8, 512, 1, false),
+    KW_VARIANT(1, 8, 32, 12, false, false),    // x <= 256
+    KW_VARIANT(2, 8, 32, 16, true, true),
+    KW_VARIANT(101, 8, 64, 6, false, false),   // x <= 512
+    KW_VARIANT(102, 8, 64, 8, true, true),
+    KW_VARIANT(103, 8, 64, 6, true, false),
+    KW_VARIANT(201, 8, 128, 3, false, false),  // x <= 1024
+    KW_VARIANT(202, 8, 128, 3, true, false),
+    KW_VARIANT(203, 8, 128, 4, true, true),
+    KW_VARIANT(204, 8, 128, 4, true, false),
+    KW_VARIANT(205, 8, 128, 3, true, true),
+    KW_VARIANT(301, 8, 256, 1, false, false),  // x <= 2048
+    KW_VARIANT(302, 8, 256, 2, true, true),
+    KW_VARIANT(401, 8, 512, 1, true, true),    // x <= 4096
+    KW_VARIANT(402, 8, 512, 1, true, false),
 };
 constexpr int kNumVariants = sizeof(g_variants) / sizeof(g_variants[0]);
 constexpr int kMaxRegX = 4096;
@@ -81,6 +83,7 @@ __global__ void status_reset_kernel(unsigned int* status)
 {
     status[0] = 0u;
     status[1] = 0xffffffffu;
+    status[2] = status[3] = status[4] = status[5] = status[6] = status[7] = 0u;
 }
 
 // BlackScholes_Pricer::priceOne (src/Pricer/kwBlackScholes.cpp:27-50) on European copies and
@@ -190,6 +193,7 @@ struct kw_fd1d_handle {
     int regs = 0;
     int last_grid = 0;
     uint64_t last_n_pde = 0;
+    unsigned int mode_count[6] = {0, 0, 0, 0, 0, 0};
 
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -325,7 +329,7 @@ int price_to_device(kw_fd1d_handle* h, const kw_option* assets, size_t n, DevBuf
                     double* d_out)
 {
     KW_CUDA(h, d_opts.reserve(n));
-    KW_CUDA(h, h->d_status.reserve(2));
+    KW_CUDA(h, h->d_status.reserve(8));
     KW_CUDA(h, cudaMemcpyAsync(d_opts.p, assets, n * sizeof(kw_option), cudaMemcpyHostToDevice, h->stream));
     Fd1dBatch B;
     memset(&B, 0, sizeof B);
@@ -336,6 +340,7 @@ int price_to_device(kw_fd1d_handle* h, const kw_option* assets, size_t n, DevBuf
     B.xDim = (int32_t)h->cfg.x_grid_size;
     B.density = h->cfg.density;
     B.scale = h->cfg.scale;
+    B.max_mode = h->cfg.exact == 0 ? 4 : (h->cfg.exact == 1 ? 1 : 0);
     if (h->cfg.compress) {
         size_t m;
         uint32_t *rep, *start, *csr;
@@ -360,9 +365,10 @@ int price_to_device(kw_fd1d_handle* h, const kw_option* assets, size_t n, DevBuf
 
 int check_status(kw_fd1d_handle* h, cudaStream_t st, const kw_option* host_assets)
 {
-    KW_CUDA(h, h->h_status.reserve(2));
-    KW_CUDA(h, cudaMemcpyAsync(h->h_status.p, h->d_status.p, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    KW_CUDA(h, h->h_status.reserve(8));
+    KW_CUDA(h, cudaMemcpyAsync(h->h_status.p, h->d_status.p, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     KW_CUDA(h, cudaStreamSynchronize(st));
+    for (int i = 0; i < 6; ++i) h->mode_count[i] = h->h_status.p[2 + i];
     if (h->h_status.p[0] != 0) {
         const unsigned int idx = h->h_status.p[1];
         if (host_assets) return fail(h, KW_FD1D_ERANGE, range_message(h, host_assets[idx]));
@@ -388,6 +394,7 @@ void kw_fd1d_config_default(kw_fd1d_config* cfg)
     cfg->layout = KW_FD1D_LAYOUT_AUTO;
     cfg->compress = 1;
     cfg->variant = 0;
+    cfg->exact = 0;
 }
 
 int kw_fd1d_create(const kw_fd1d_config* cfg, kw_fd1d_handle** out)
@@ -401,6 +408,8 @@ int kw_fd1d_create(const kw_fd1d_config* cfg, kw_fd1d_handle** out)
         return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::init: FD1D.T_GRID_SIZE must be >= 2 and FD1D.X_GRID_SIZE >= 3");
     if (!(cfg->density > 0) || !(cfg->scale > 0))
         return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::init: FD1D.DENSITY and FD1D.SCALE must be positive");
+    if (cfg->exact < 0 || cfg->exact > 2)
+        return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::init: FD1D.GPU.EXACT must be 0, 1 or 2");
     if (cfg->precision != KW_FD1D_F64)
         return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::init: only FD1D.GPU.PRECISION = f64 is built in this round");
 
@@ -448,8 +457,8 @@ int kw_fd1d_create(const kw_fd1d_config* cfg, kw_fd1d_handle** out)
     KW_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     KW_CUDA(h, cudaEventCreate(&h->ev0));
     KW_CUDA(h, cudaEventCreate(&h->ev1));
-    KW_CUDA(h, h->d_status.reserve(2));
-    KW_CUDA(h, h->h_status.reserve(2));
+    KW_CUDA(h, h->d_status.reserve(8));
+    KW_CUDA(h, h->h_status.reserve(8));
     return KW_FD1D_OK;
 }
 
@@ -534,6 +543,7 @@ int kw_fd1d_price_device(kw_fd1d_handle* h, const kw_option* d_assets, size_t n,
     B.xDim = (int32_t)h->cfg.x_grid_size;
     B.density = h->cfg.density;
     B.scale = h->cfg.scale;
+    B.max_mode = h->cfg.exact == 0 ? 4 : (h->cfg.exact == 1 ? 1 : 0);
     return launch_batch(h, B, (cudaStream_t)stream);
 }
 
@@ -564,6 +574,7 @@ int kw_fd1d_get_info(const kw_fd1d_handle* hc, kw_fd1d_info* info)
     info->grid = h->last_grid;
     info->sm_clock_khz = h->clock_khz;
     info->last_n_pde = h->last_n_pde;
+    for (int i = 0; i < 6; ++i) info->mode_count[i] = h->mode_count[i];
     info->last_kernel_ms = 0.;
     if (h->ev_valid && cudaEventSynchronize(h->ev1) == cudaSuccess) {
         float ms = 0.f;

@@ -30,11 +30,13 @@ struct Fd1dBatch {
     const uint32_t* csr_start;
     const uint32_t* csr_opt;
     double* prices;
-    unsigned int* status;  // [0] = number of out-of-range options, [1] = smallest such index
+    unsigned int* status;  // [0] = number of out-of-range options, [1] = smallest such index,
+                           // [2..6] = PDEs marched in carry mode 0..4 (layout B)
     uint32_t n_pde;
     uint32_t pde_base;     // first PDE of this launch (layout A chunks the batch)
     int32_t tDim;
     int32_t xDim;
+    int32_t max_mode;      // layout B: highest carry-truncation mode allowed (4 = all, 0 = exact)
     double density;
     double scale;
 };

@@ -1,5 +1,5 @@
 // fd1d_reg.cuh -- Layout B: one CTA per PDE, the whole time march in one launch, x-grid
-// coefficients in REGISTERS (payoff, and optionally one fix-up array, in shared memory).
+// coefficients in REGISTERS (optionally the payoff and one fix-up array in shared memory).
 //
 // Replaces Fd1d::solve/solveOne + solveTridiagonal + Fd1d::value of the reference
 // (src/Math/kwFd1d.cpp:11-158, src/Math/kwMath.cpp:16-49) and the grid/payoff set-up of
@@ -7,18 +7,25 @@
 // parameters in, 8 B per priced option out.
 //
 // Partitioned Thomas ("SPIKE" with time-invariant spikes).  Thread k of P owns the M
-// contiguous nodes k*M .. k*M+M-1.  Because the LU factors never change, the two sweeps are
-// first-order linear recurrences with constant multipliers, so for thread k
-//     y~_i = yl_i + Pp_i * Yin_k                  (yl: local forward sweep from 0)
+// contiguous nodes k*M .. k*M+M-1 ("chunk k").  Because the LU factors never change, the two
+// sweeps are first-order linear recurrences with constant multipliers, so for chunk k
+//     y~_i = yl_i + Pp_i * Yin_k                  (yl: local forward sweep started from 0)
 //     u~_i = ul_i + R_i * Yin_k + Q_i * Uin_k      (ul: local backward sweep of yl)
 // where Pp (prefix products of a~), Q (suffix products of g~) and R (backward sweep of Pp)
 // are precomputed, and Yin_k / Uin_k -- the true sweep values just outside the chunk -- come
 // from two warp-level Kogge-Stone scans with precomputed multipliers (5 shuffle+FMA levels
-// each) plus ONE __syncthreads per time step for the cross-warp carries: the backward scan is
-// started with the warp-local forward carry and corrected afterwards with the precomputed
-// response H of the backward scan to the cross-warp forward carry.
-// Per node-step: 2 local-sweep FMAs + 3 fix-up FMAs + 1 max; per thread-step ~25 scan FMAs.
+// each) plus ONE __syncthreads per time step for the cross-warp carries:
+//   * forward scan  S_k  = yl_end[k] + A_k S_{k-1}            (inclusive, lanes of one warp)
+//   * backward scan on SHIFTED lanes: lane k holds chunk k+1's value,
+//         T_k = (ul_0[k+1] + R0[k+1] S_k) + G_{k+1} T_{k+1},
+//     so T_k is directly Uin_k and only the inclusive S_k is on the critical path;
+//   * the cross-warp forward carry X_w enters the backward scan linearly through the
+//     precomputed response H, so both warp-boundary values are exchanged at the same barrier
+//     and every warp evaluates its two carries as dot products with precomputed rows.
+// Per node-step: 2 local-sweep FMAs + 3 fix-up FMAs + 1 compare/select.
 #pragma once
+#include <type_traits>
+
 #include "fd1d_common.cuh"
 
 namespace kwfd1d {
@@ -29,12 +36,15 @@ template <int M, int P>
 struct RegSmem {
     static constexpr int N = M * P;
     static constexpr int NW = P / 32;
+    static constexpr int NWP = (NW + 1) & ~1;  // padded to even for 16-byte loads
     static constexpr int SCRATCH = (N > 8 * P) ? N : 8 * P;
-    // doubles: xs[N] | scratch[SCRATCH] | proj[N] | dq[N] (optional) | per-warp tables
-    static constexpr int WARP_TAB = 3 * NW + 4 * NW;  // AWf, AWb, H0, zf[2][NW], zb[2][NW]
-    static constexpr size_t bytes(bool dq_smem)
+    // per-warp exchange tables (doubles): rows cf, cb, ce [NW][NWP]; zf, zb [2][NWP]; AWf, AWb, H0 [NW]
+    static constexpr int ZS = (NW + 2) * 32;   // exchange slots per parity buffer: [warp -1 .. NW][lane], pads stay 0
+    static constexpr int WARP_TAB = 3 * NW * NWP + 2 * ZS + 3 * NW + 2 * P + 4;
+    // doubles: xs[N] | scratch[SCRATCH] | proj[N] (optional) | dq[N] (optional) | tables
+    static constexpr size_t bytes(bool proj_smem, bool dq_smem)
     {
-        return sizeof(double) * (size_t)(N + SCRATCH + N + (dq_smem ? N : 0) + WARP_TAB + 8);
+        return sizeof(double) * (size_t)(N + SCRATCH + (proj_smem ? N : 0) + (dq_smem ? N : 0) + WARP_TAB);
     }
 };
 
@@ -72,35 +82,66 @@ __device__ __forceinline__ Mat2 mat_shfl_up(const Mat2& a, int d)
     return r;
 }
 
-// DQ_SMEM: keep the D*Q fix-up array in shared memory instead of registers (lower register
-// count -> one more CTA per SM, at the price of shared-memory bandwidth).
-template <int M, int P, int MINB, bool DQ_SMEM>
+// Explicit shared-space accesses for the time loop: a 32-bit shared address kept in a register
+// (generic pointers made ptxas re-derive the shared window base with S2UR inside the loop).
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ double lds_f64(uint32_t a)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ double2 lds_v2f64(uint32_t a)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v)
+{
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+
+// std::max(v, payoff) of the reference (src/Math/kwFd1d.cpp:131): (a < b) ? b : a.
+// One DSETP + two selects; fmax() would add NaN canonicalisation the scheme does not need.
+__device__ __forceinline__ double max_like_std(double a, double b) { return (a < b) ? b : a; }
+
+// PROJ_SMEM / DQ_SMEM: keep the projection floor / the D*Q fix-up array in shared memory
+// instead of registers (fewer registers -> more CTAs per SM, more shared-memory wavefronts).
+template <int M, int P, int MINB, bool PROJ_SMEM, bool DQ_SMEM>
 __global__ void __launch_bounds__(P, MINB) fd1d_reg_kernel(const Fd1dBatch B)
 {
     static_assert(M % 2 == 0 && P % 32 == 0, "M even, whole warps");
     using L = RegSmem<M, P>;
     constexpr int N = L::N;
     constexpr int NW = L::NW;
+    constexpr int NWP = L::NWP;
+    constexpr int ZS = L::ZS;
     constexpr int M2 = M / 2;
 
     extern __shared__ double smem[];
-    double* xs = smem;                                   // x grid, natural order
-    double* scr = xs + N;                                // set-up exchange, then final v
+    double* xs = smem;    // x grid, natural order
+    double* scr = xs + N; // set-up exchange, then the final v
     double2* proj2 = reinterpret_cast<double2*>(scr + L::SCRATCH);  // [M2][P] pairs
-    double2* dq2 = reinterpret_cast<double2*>(scr + L::SCRATCH + N);
-    double* tab = scr + L::SCRATCH + N + (DQ_SMEM ? N : 0);
-    double* AWf = tab;            // product of forward chunk multipliers over warp w
-    double* AWb = tab + NW;       // same, backward
-    double* H0 = tab + 2 * NW;    // response of warp w's first backward value to its forward carry
-    double* zf = tab + 3 * NW;    // [2][NW] warp-end forward values, double-buffered by step parity
-    double* zb = tab + 5 * NW;    // [2][NW] warp-start backward values
+    double2* dq2 = reinterpret_cast<double2*>(scr + L::SCRATCH + (PROJ_SMEM ? N : 0));
+    double* tab = scr + L::SCRATCH + (PROJ_SMEM ? N : 0) + (DQ_SMEM ? N : 0);
+    double* t_cf = tab;                  // [NW][NWP]  X_w  = sum_w' cf[w][w'] zf[w']
+    double* t_cb = t_cf + NW * NWP;      // [NW][NWP]  Xb_w = sum_w' cb[w][w'] zb[w'] + ce[w][w'] zf[w']
+    double* t_ce = t_cb + NW * NWP;      // [NW][NWP]
+    double* zx = t_ce + NW * NWP;        // [2][NW + 2][32] exchange slots, double-buffered by step parity:
+                                         // lane 31's slot = warp-end forward value, lane 0's = warp-start backward value
+    double* AWf = zx + 2 * ZS;           // [NW] product of the forward chunk multipliers of warp w
+    double* AWb = AWf + NW;              // [NW] same, backward
+    double* H0 = AWb + NW;               // [NW] response of warp w's first backward value to X_w
+    double* s_af4 = H0 + NW;             // [P] level-4 forward multipliers (general mode only)
+    double* s_gb4 = s_af4 + P;           // [P] level-4 backward multipliers (general mode only)
 
     // scratch sub-arrays used during set-up
-    double* s_bu_last = scr;          // [P]
-    double* s_mat = scr + P;          // [4][P]
-    double* s_bin = scr + 5 * P;      // [P] pivot just before each chunk
-    double* s_ib_first = scr + 6 * P; // [P]
-    double* s_ib_last = scr + 7 * P;  // [P]
+    double* s_bu_last = scr;           // [P]
+    double* s_mat = scr + P;           // [4][P]
+    double* s_bin = scr + 5 * P;       // [P] pivot just before each chunk
+    double* s_ib_first = scr + 6 * P;  // [P]
+    double* s_ib_last = scr + 7 * P;   // [P]
 
     const int k = threadIdx.x;
     const int lane = k & 31;
@@ -114,20 +155,19 @@ __global__ void __launch_bounds__(P, MINB) fd1d_reg_kernel(const Fd1dBatch B)
         const PdeScalars sc = pde_scalars(opt, B);
 
         // ---------------- set-up: grid, payoff --------------------------------------------
-        double v[M];
-        {
-            double pj[M];
+        double v[M], pj[M];
 #pragma unroll
-            for (int i = 0; i < M; ++i) {
-                const int j = k * M + i;
-                const double x = x_node(sc, B.density, j);
-                xs[j] = x;
-                double p = 0.;
-                if (j < xDim) p = payoff_node(sc.put, x);
-                v[i] = p;
-                // projection skips the last node (src/Math/kwFd1d.cpp:130); European: never
-                pj[i] = (sc.american && j < xDim - 1) ? p : -CUDART_INF;
-            }
+        for (int i = 0; i < M; ++i) {
+            const int j = k * M + i;
+            const double x = x_node(sc, B.density, j);
+            xs[j] = x;
+            double p = 0.;
+            if (j < xDim) p = payoff_node(sc.put, x);
+            v[i] = p;
+            // projection skips the last node (src/Math/kwFd1d.cpp:130); European: never
+            pj[i] = (sc.american && j < xDim - 1) ? p : -CUDART_INF;
+        }
+        if (PROJ_SMEM) {
 #pragma unroll
             for (int c = 0; c < M2; ++c) proj2[c * P + k] = make_double2(pj[2 * c], pj[2 * c + 1]);
         }
@@ -136,7 +176,7 @@ __global__ void __launch_bounds__(P, MINB) fd1d_reg_kernel(const Fd1dBatch B)
         // ---------------- B rows, Moebius-composed pivots ---------------------------------
         double a[M], g[M], D[M];  // a~ (a[0] = chunk-entry multiplier), g~ (g[M-1] = chunk-exit), 2/beta
         double DR[M], DQ[M];
-        double Af[5], Gb[5], PWexf, PWexb, R0, Hp1;
+        double Af[4], Gb[4], PWexf, PWbs, R0n, Hs, G0;
         {
             double bl[M], bb[M], bu[M];
 #pragma unroll
@@ -232,6 +272,7 @@ __global__ void __launch_bounds__(P, MINB) fd1d_reg_kernel(const Fd1dBatch B)
             }
         }
         // spikes: Pp prefix products of a~, Q suffix products of g~, R = backward sweep of Pp
+        bool bad_far = false, bad_l4 = false, bad_l3 = false, bad_l2 = false;  // "not negligible" votes
         {
             double Pp[M], Q[M], R[M];
             Pp[0] = a[0];
@@ -248,129 +289,278 @@ __global__ void __launch_bounds__(P, MINB) fd1d_reg_kernel(const Fd1dBatch B)
                 DR[i] = D[i] * R[i];
                 DQ[i] = D[i] * Q[i];
             }
-            R0 = R[0];
-            // Kogge-Stone multipliers inside the warp (forward: chunk products A = Pp[M-1])
+            // ---- forward Kogge-Stone multipliers (chunk products A_k = Pp[M-1])
             double A = Pp[M - 1];
+            double af4 = 0., gb4 = 0.;
 #pragma unroll
             for (int d = 0; d < 5; ++d) {
                 const int s = 1 << d;
                 const double o = __shfl_up_sync(FULL, A, s);
-                Af[d] = lane >= s ? A : 0.;
+                const double m = lane >= s ? A : 0.;
+                if (d < 4)
+                    Af[d] = m;
+                else
+                    af4 = m;
                 if (lane >= s) A *= o;
             }
+            const double PWf = A;  // product warp-start .. k (inclusive)
             {
                 const double ex = __shfl_up_sync(FULL, A, 1);
                 PWexf = lane ? ex : 1.;
             }
             if (lane == 31) AWf[warp] = A;
-            double G = Q[0];
-#pragma unroll
-            for (int d = 0; d < 5; ++d) {
-                const int s = 1 << d;
-                const double o = __shfl_down_sync(FULL, G, s);
-                Gb[d] = lane < 32 - s ? G : 0.;
-                if (lane < 32 - s) G *= o;
-            }
+            // ---- backward scan on shifted lanes: lane k carries chunk k+1
+            G0 = Q[0];  // this chunk's backward multiplier
+            const double R0 = R[0];
             {
-                const double ex = __shfl_down_sync(FULL, G, 1);
-                PWexb = lane < 31 ? ex : 1.;
-            }
-            if (lane == 0) AWb[warp] = G;
-            // H: backward in-warp scan of the response R0 * PWexf to a unit cross-warp forward carry
-            double H = R0 * PWexf;
+                const double gn = __shfl_down_sync(FULL, G0, 1);
+                const double rn = __shfl_down_sync(FULL, R0, 1);
+                R0n = lane < 31 ? rn : 0.;
+                double G = lane < 31 ? gn : 0.;  // Gn_k = G_{k+1}
 #pragma unroll
-            for (int d = 0; d < 5; ++d) {
-                const double o = __shfl_down_sync(FULL, H, 1 << d);
-                H = fma(Gb[d], o, H);
+                for (int d = 0; d < 5; ++d) {
+                    const int s = 1 << d;
+                    const double o = __shfl_down_sync(FULL, G, s);
+                    const double m = lane < 32 - s ? G : 0.;
+                    if (d < 4)
+                        Gb[d] = m;
+                    else
+                        gb4 = m;
+                    if (lane < 32 - s) G *= o;
+                }
+                // G = prod_{i=k}^{31} Gn_i, which is 0 through Gn_31 = 0; the carry multiplier
+                // PWbs_k = prod_{i=k}^{30} Gn_i needs the product without that last factor
+                double Gx = lane < 31 ? gn : 1.;
+#pragma unroll
+                for (int d = 0; d < 5; ++d) {
+                    const int s = 1 << d;
+                    const double o = __shfl_down_sync(FULL, Gx, s);
+                    if (lane < 32 - s) Gx *= o;
+                }
+                PWbs = Gx;  // lane 31: 1
+                // Hs: shifted backward scan of the response R0n * PWf to a unit forward carry X_w
+                double H = R0n * PWf;
+#pragma unroll
+                for (int d = 0; d < 5; ++d) {
+                    const double o = __shfl_down_sync(FULL, H, 1 << d);
+                    H = fma(d < 4 ? Gb[d] : gb4, o, H);
+                }
+                Hs = H;
+                if (lane == 0) {
+                    AWb[warp] = G0 * PWbs;       // prod_{j=0}^{31} G_j
+                    H0[warp] = fma(G0, Hs, R0);  // d(T_0)/d(X_w)
+                }
             }
-            {
-                const double nx = __shfl_down_sync(FULL, H, 1);
-                Hp1 = lane < 31 ? nx : 0.;
-            }
-            if (lane == 0) H0[warp] = H;
+            s_af4[k] = af4;
+            s_gb4[k] = gb4;
             if (DQ_SMEM) {
 #pragma unroll
                 for (int c = 0; c < M2; ++c) dq2[c * P + k] = make_double2(DQ[2 * c], DQ[2 * c + 1]);
             }
+            // ---- negligibility votes (DESIGN.md "Truncation").  A carry term may be dropped when its
+            // absolute size, relative to the local solution scale max(1, e^x), accumulated over all
+            // time steps, stays below 2^-56: |multiplier| * Bmax * growth * tDim <= 2^-56, where
+            // Bmax bounds the pivot scaling of the carried values and growth = 1 for puts (|v| <= 1)
+            // and e^(x_source - x_here) for calls (v <= e^x) in the backward direction.
+            double bmax = 0.;
+#pragma unroll
+            for (int i = 0; i < M; ++i) bmax = fmax(bmax, D[i] != 0. ? fabs(2. / D[i]) : 1.);
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) bmax = fmax(bmax, __shfl_xor_sync(FULL, bmax, d));
+            if (lane == 0) scr[warp] = bmax;  // scr is free again (all set-up exchanges are done)
+            __syncthreads();
+            bmax = scr[0];
+#pragma unroll
+            for (int w = 1; w < NW; ++w) bmax = fmax(bmax, scr[w]);
+            const double tol = 0x1p-56 / (bmax * (double)B.tDim);
+            const int j_src = min((warp + 1) * 32 * M + M - 1, xDim - 1);
+            const double growth =
+                sc.put ? 1. : exp(fmax(0., xs[j_src]) - fmax(0., xs[min(k * M, xDim - 1)]));
+            bad_l4 = !(fabs(af4) <= tol) || !(fabs(gb4) * growth <= tol);
+            bad_l3 = !(fabs(Af[3]) <= tol) || !(fabs(Gb[3]) * growth <= tol);
+            bad_l2 = !(fabs(Af[2]) <= tol) || !(fabs(Gb[2]) * growth <= tol);
+            if (lane == 31) bad_far = !(fabs(A) <= tol);
+            if (lane == 0) {
+                const double gfar = sc.put ? 1. : exp(fmax(0., xs[xDim - 1]) - fmax(0., xs[min(k * M, xDim - 1)]));
+                bad_far = !(fabs(G0 * PWbs) * gfar <= tol);
+            }
         }
+        const int any_far = __syncthreads_or(bad_far);
+        const int any_l4 = __syncthreads_or(bad_l4);
+        const int any_l3 = __syncthreads_or(bad_l3);
+        const int any_l2 = __syncthreads_or(bad_l2);
+        // carry modes.  0: every carry term; 1: only nearest-warp carries, all 5 scan levels;
+        // 2 / 3 / 4: nearest-warp carries and 4 / 3 / 2 scan levels (higher levels proven negligible).
+        // B.max_mode caps it (FD1D.GPU.EXACT = 2 -> mode 0 everywhere, 1 -> at most mode 1).
+        int mode = 0;
+        if (!(NW > 1 && any_far)) mode = any_l4 ? 1 : (any_l3 ? 2 : (any_l2 ? 3 : 4));
+        if (mode > B.max_mode) mode = B.max_mode;
+        if (NW == 1 && mode == 0) mode = 1;  // no cross-warp carries to be exact about
+        // cross-warp rows (mode 0 only): thread w < NW fills row w
+        if (NW > 1 && mode == 0) {
+            if (k < NW) {
+                const int w = k;
+                // cf[w][w'] = prod_{w' < w'' < w} AWf[w'']  (w' < w), else 0
+                double c = 1.;
+                for (int wp = NWP - 1; wp >= 0; --wp) {
+                    double val = 0.;
+                    if (wp < w) {
+                        val = c;
+                        c *= AWf[wp];
+                    }
+                    t_cf[w * NWP + wp] = val;
+                }
+                // cb[w][w'] = prod_{w < w'' < w'} AWb[w'']  (w' > w), else 0
+                c = 1.;
+                for (int wp = 0; wp < NWP; ++wp) {
+                    double val = 0.;
+                    if (wp > w && wp < NW) {
+                        val = c;
+                        c *= AWb[wp];
+                    }
+                    t_cb[w * NWP + wp] = val;
+                }
+            }
+            __syncthreads();
+            if (k < NW) {
+                const int w = k;
+                // ce[w][w''] = sum_{w' > max(w, w'')} cb[w][w'] * H0[w'] * cf[w'][w'']
+                for (int ws = 0; ws < NWP; ++ws) {
+                    double acc = 0.;
+                    for (int wp = (w > ws ? w : ws) + 1; wp < NW; ++wp)
+                        acc = fma(t_cb[w * NWP + wp] * H0[wp], t_cf[wp * NWP + ws], acc);
+                    t_ce[w * NWP + ws] = acc;
+                }
+            }
+        }
+        // exchange slots, zero pads for the edge warps (slot rows 0 and NW + 1 of both buffers)
+        for (int i = k; i < 2 * ZS; i += P) zx[i] = 0.;
         __syncthreads();
+        const double H0n = (NW > 1 && warp < NW - 1) ? H0[warp + 1] : 0.;
+        const uint32_t a_proj = smem_addr(proj2 + k);
+        const uint32_t a_dq = smem_addr(dq2 + k);
+        const uint32_t a_mine = smem_addr(zx + (warp + 1) * 32 + lane);  // this lane's slot, parity 0
+        const uint32_t a_zx = smem_addr(zx);
+        const uint32_t a_rows = smem_addr(t_cf + warp * NWP);
 
         // ---------------- time march: tDim-1 steps, one barrier each ----------------------
-        for (int step = 0; step < nsteps; ++step) {
+        auto march = [&](auto mode_c) {
+            constexpr int MODE = decltype(mode_c)::value;
+            constexpr int NLEV = MODE <= 1 ? 5 : 6 - MODE;  // scan levels kept
+            double af4 = 0., gb4 = 0.;
+            if (NLEV == 5) {
+                af4 = s_af4[k];
+                gb4 = s_gb4[k];
+            }
+            // local forward sweep from 0 for the first step (later ones are fused into the loop tail)
             double y[M];
             y[0] = v[0];
 #pragma unroll
             for (int i = 1; i < M; ++i) y[i] = fma(a[i], y[i - 1], v[i]);
-            double S = y[M - 1];
+            for (int step = 0; step < nsteps; ++step) {
+                // inclusive forward scan of the chunk-end values inside the warp
+                double S = y[M - 1];
 #pragma unroll
-            for (int d = 0; d < 5; ++d) {
-                const double o = __shfl_up_sync(FULL, S, 1 << d);
-                S = fma(Af[d], o, S);
-            }
-            double Sm1 = __shfl_up_sync(FULL, S, 1);
-            if (lane == 0) Sm1 = 0.;
-            // local backward sweep of the local forward result
+                for (int d = 0; d < 4; ++d) {
+                    if (d < NLEV) {
+                        const double o = __shfl_up_sync(FULL, S, 1 << d);
+                        S = fma(Af[d], o, S);
+                    }
+                }
+                if (NLEV == 5) {
+                    const double o = __shfl_up_sync(FULL, S, 16);
+                    S = fma(af4, o, S);
+                }
+                // local backward sweep of the local forward result; r_i = D_i ul_i - v_i on the fly
 #pragma unroll
-            for (int i = M - 2; i >= 0; --i) y[i] = fma(g[i], y[i + 1], y[i]);
-            double T = fma(R0, Sm1, y[0]);
+                for (int i = M - 2; i >= 0; --i) y[i] = fma(g[i], y[i + 1], y[i]);
 #pragma unroll
-            for (int d = 0; d < 5; ++d) {
-                const double o = __shfl_down_sync(FULL, T, 1 << d);
-                T = fma(Gb[d], o, T);
-            }
-            double Tp1 = __shfl_down_sync(FULL, T, 1);
-            if (lane == 31) Tp1 = 0.;
+                for (int i = 0; i < M; ++i) v[i] = fma(D[i], y[i], -v[i]);
+                // shifted backward scan: lane k holds chunk k+1
+                const double uln = __shfl_down_sync(FULL, y[0], 1);
+                double T = fma(R0n, S, lane < 31 ? uln : 0.);
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    if (d < NLEV) {
+                        const double o = __shfl_down_sync(FULL, T, 1 << d);
+                        T = fma(Gb[d], o, T);
+                    }
+                }
+                if (NLEV == 5) {
+                    const double o = __shfl_down_sync(FULL, T, 16);
+                    T = fma(gb4, o, T);
+                }
+                double Sm1 = __shfl_up_sync(FULL, S, 1);
+                if (lane == 0) Sm1 = 0.;
 
-            double Xw = 0., Xbw = 0.;
-            if (NW > 1) {
-                const int par = (step & 1) * NW;
-                if (lane == 31) zf[par + warp] = S;
-                if (lane == 0) zb[par + warp] = T;
-                __syncthreads();
-                // forward carries into every warp, then the corrected backward warp-start
-                // values, then the backward carry into this warp
-                double Xs[NW];
-                double X = 0.;
+                double Xw = 0., Xbw = 0.;
+                if (NW > 1) {
+                    // every lane stores (no divergent branch); only lanes 0 and 31 are read back
+                    const uint32_t par = (uint32_t)(step & 1) * (ZS * 8);
+                    sts_f64(a_mine + par, lane == 0 ? fma(G0, T, y[0]) : S);
+                    __syncthreads();
+                    const uint32_t zrow = a_zx + par + (uint32_t)warp * 256;  // slot row of warp - 1
+                    if (MODE == 0) {
 #pragma unroll
-                for (int w = 0; w < NW; ++w) {
-                    Xs[w] = X;
-                    if (w == warp) Xw = X;
-                    X = fma(AWf[w], X, zf[par + w]);
+                        for (int w = 0; w < NW; ++w) {
+                            const double f = lds_f64(a_zx + par + (w + 1) * 256 + 31 * 8);
+                            const double b = lds_f64(a_zx + par + (w + 1) * 256);
+                            const double cf = lds_f64(a_rows + w * 8);
+                            const double cb = lds_f64(a_rows + (NW * NWP + w) * 8);
+                            const double ce = lds_f64(a_rows + (2 * NW * NWP + w) * 8);
+                            Xw = fma(cf, f, Xw);
+                            Xbw = fma(cb, b, Xbw);
+                            Xbw = fma(ce, f, Xbw);
+                        }
+                    } else {
+                        // nearest-warp carries only: X_w = zf[w-1]; Xb_w = zb[w+1] + H0[w+1] * zf[w]
+                        const double fm1 = lds_f64(zrow + 31 * 8);
+                        const double fw = lds_f64(zrow + 256 + 31 * 8);
+                        const double bp1 = lds_f64(zrow + 512);
+                        Xw = fm1;
+                        Xbw = fma(H0n, fw, bp1);
+                    }
                 }
-                double Xb = 0.;
+                const double Yin = fma(PWexf, Xw, Sm1);
+                const double Uin = fma(PWbs, Xbw, fma(Hs, Xw, T));
+                // fix-up + projection, fused with the NEXT step's local forward sweep so that the
+                // sweep's dependent chain hides behind the independent per-node fix-ups
 #pragma unroll
-                for (int w = NW - 1; w >= 0; --w) {
-                    if (w == warp) Xbw = Xb;
-                    const double zt = fma(Xs[w], H0[w], zb[par + w]);
-                    Xb = fma(AWb[w], Xb, zt);
+                for (int c = 0; c < M2; ++c) {
+                    double2 pp, qq;
+                    if (PROJ_SMEM)
+                        pp = lds_v2f64(a_proj + c * (P * 16));
+                    else
+                        pp = make_double2(pj[2 * c], pj[2 * c + 1]);
+                    if (DQ_SMEM)
+                        qq = lds_v2f64(a_dq + c * (P * 16));
+                    else
+                        qq = make_double2(DQ[2 * c], DQ[2 * c + 1]);
+                    {
+                        const int i = 2 * c;
+                        double r = fma(DR[i], Yin, v[i]);
+                        r = fma(qq.x, Uin, r);
+                        v[i] = max_like_std(r, pp.x);
+                        y[i] = i ? fma(a[i], y[i - 1], v[i]) : v[i];
+                    }
+                    {
+                        const int i = 2 * c + 1;
+                        double r = fma(DR[i], Yin, v[i]);
+                        r = fma(qq.y, Uin, r);
+                        v[i] = max_like_std(r, pp.y);
+                        y[i] = fma(a[i], y[i - 1], v[i]);
+                    }
                 }
             }
-            const double Yin = fma(PWexf, Xw, Sm1);
-            const double Uin = fma(PWexb, Xbw, fma(Hp1, Xw, Tp1));
-#pragma unroll
-            for (int c = 0; c < M2; ++c) {
-                const double2 pp = proj2[c * P + k];
-                double2 qq;
-                if (DQ_SMEM)
-                    qq = dq2[c * P + k];
-                else
-                    qq = make_double2(DQ[2 * c], DQ[2 * c + 1]);
-                {
-                    const int i = 2 * c;
-                    double r = fma(D[i], y[i], -v[i]);
-                    r = fma(DR[i], Yin, r);
-                    r = fma(qq.x, Uin, r);
-                    v[i] = fmax(r, pp.x);
-                }
-                {
-                    const int i = 2 * c + 1;
-                    double r = fma(D[i], y[i], -v[i]);
-                    r = fma(DR[i], Yin, r);
-                    r = fma(qq.y, Uin, r);
-                    v[i] = fmax(r, pp.y);
-                }
-            }
+        };
+        switch (mode) {
+            case 0: march(std::integral_constant<int, 0>{}); break;
+            case 1: march(std::integral_constant<int, 1>{}); break;
+            case 2: march(std::integral_constant<int, 2>{}); break;
+            case 3: march(std::integral_constant<int, 3>{}); break;
+            default: march(std::integral_constant<int, 4>{}); break;
         }
+        if (k == 0) atomicAdd(&B.status[2 + mode], 1u);
 
         // ---------------- epilogue: interpolate every option of this chain -----------------
         __syncthreads();

@@ -35,7 +35,7 @@ class _CConfig(C.Structure):  # struct kw_fd1d_config
     _fields_ = [("density", C.c_double), ("scale", C.c_double), ("t_grid_size", C.c_int64),
                 ("x_grid_size", C.c_int64), ("device", C.c_int32), ("precision", C.c_int32),
                 ("layout", C.c_int32), ("compress", C.c_int32), ("variant", C.c_int32),
-                ("reserved", C.c_int32 * 3)]
+                ("exact", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 class _CInfo(C.Structure):  # struct kw_fd1d_info
@@ -43,7 +43,7 @@ class _CInfo(C.Structure):  # struct kw_fd1d_info
                 ("threads_per_pde", C.c_int32), ("nodes_per_thread", C.c_int32), ("ctas_per_sm", C.c_int32),
                 ("regs_per_thread", C.c_int32), ("smem_per_cta", C.c_int32), ("grid", C.c_int32),
                 ("sm_clock_khz", C.c_int32), ("reserved", C.c_int32), ("last_kernel_ms", C.c_double),
-                ("last_n_pde", C.c_uint64), ("device_name", C.c_char * 128)]
+                ("last_n_pde", C.c_uint64), ("mode_count", C.c_uint32 * 6), ("device_name", C.c_char * 128)]
 
 
 _lib = None
@@ -145,7 +145,8 @@ class Fd1dGpu_Pricer(Pricer):
     Keys (init): FD1D.DENSITY, FD1D.SCALE, FD1D.T_GRID_SIZE, FD1D.X_GRID_SIZE exactly as the
     reference (src/Pricer/kwFd1d.cpp:12-16) plus FD1D.GPU.DEVICE (int), FD1D.GPU.LAYOUT
     ("auto"|"reg"|"soa"), FD1D.GPU.PRECISION ("f64"), FD1D.GPU.COMPRESS (int 0/1),
-    FD1D.GPU.VARIANT (int)."""
+    FD1D.GPU.VARIANT (int), FD1D.GPU.EXACT (int 0/1/2: 0 lets provably negligible carry terms be
+    dropped, 2 keeps every term)."""
 
     _mode_bs = False
 
@@ -173,6 +174,7 @@ class Fd1dGpu_Pricer(Pricer):
         c.precision = PRECISIONS[prec]
         c.compress = config.get("FD1D.GPU.COMPRESS", 1)
         c.variant = config.get("FD1D.GPU.VARIANT", 0)
+        c.exact = config.get("FD1D.GPU.EXACT", 0)
         h = C.c_void_p()
         rc = self._lib.kw_fd1d_create(C.byref(c), C.byref(h))
         if rc != KW_FD1D_OK:
@@ -215,6 +217,7 @@ class Fd1dGpu_Pricer(Pricer):
         self._lib.kw_fd1d_get_info(self._h, C.byref(i))
         d = {f[0]: getattr(i, f[0]) for f in _CInfo._fields_ if f[0] != "reserved"}
         d["device_name"] = i.device_name.decode()
+        d["mode_count"] = list(i.mode_count)[:5]
         d["layout"] = {v: k for k, v in LAYOUTS.items()}.get(i.layout, str(i.layout))
         return d
 
