@@ -457,11 +457,14 @@ __global__ void __launch_bounds__(P, MINB) fd1d_reg_kernel(const Fd1dBatch B)
             y[0] = v[0];
 #pragma unroll
             for (int i = 1; i < M; ++i) y[i] = fma(a[i], y[i - 1], v[i]);
+            // software pipeline: the level-0 shuffle of the forward scan is issued at the END of the
+            // previous iteration, so the local backward sweep runs in its shadow
+            double o0 = __shfl_up_sync(FULL, y[M - 1], 1);
             for (int step = 0; step < nsteps; ++step) {
                 // inclusive forward scan of the chunk-end values inside the warp
-                double S = y[M - 1];
+                double S = fma(Af[0], o0, y[M - 1]);
 #pragma unroll
-                for (int d = 0; d < 4; ++d) {
+                for (int d = 1; d < 4; ++d) {
                     if (d < NLEV) {
                         const double o = __shfl_up_sync(FULL, S, 1 << d);
                         S = fma(Af[d], o, S);
@@ -551,6 +554,7 @@ __global__ void __launch_bounds__(P, MINB) fd1d_reg_kernel(const Fd1dBatch B)
                         y[i] = fma(a[i], y[i - 1], v[i]);
                     }
                 }
+                o0 = __shfl_up_sync(FULL, y[M - 1], 1);
             }
         };
         switch (mode) {
