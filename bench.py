@@ -43,13 +43,16 @@ def parse():
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--layout", default="auto", choices=["auto", "reg", "soa"])
     ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--precision", default="f64", choices=["f64", "f32"],
+                    help="f32 = fp64 set-up + fp32 march (config 3 sweeps); the headline metric is f64")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=0, help="options in the CPU baseline sample (0 = auto)")
     return ap.parse_args()
 
 
 def workload_name(a):
-    return f"synthetic {a.n} American puts/GPU, fp64, x={a.x} t={a.t}, mt19937_64 seed {a.seed}+rank (BASELINE configs[1])"
+    prec = "fp64" if a.precision == "f64" else "fp32 march (fp64 set-up)"
+    return f"synthetic {a.n} American puts/GPU, {prec}, x={a.x} t={a.t}, mt19937_64 seed {a.seed}+rank (BASELINE configs[1])"
 
 
 def flops_per_option(x, t):
@@ -205,6 +208,7 @@ def main():
     cfg.set("FD1D.GPU.DEVICE", local_rank)
     cfg.set("FD1D.GPU.LAYOUT", a.layout)
     cfg.set("FD1D.GPU.VARIANT", a.variant)
+    cfg.set("FD1D.GPU.PRECISION", a.precision)
     err, pricer = kwfd1d.PricerFactory.create(cfg)
     if err:
         raise SystemExit("bench.py: " + err)
@@ -319,7 +323,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
+            "dtype": a.precision, "data": "synthetic",
             "config": {"workload": workload_name(a), "x": a.x, "t": a.t, "options_per_gpu": n,
                        "layout": info["layout"], "variant": info["variant"],
                        "threads_per_pde": info["threads_per_pde"], "ctas_per_sm": info["ctas_per_sm"],

@@ -141,6 +141,20 @@ int kw_fd1d_fp64_peak(int32_t device, double* tflops, double* sm_mhz_effective);
  * 64-bit __shfl_up, __syncthreads with 4 warps, LDS.  out[8]. */
 int kw_fd1d_microbench(int32_t device, double* out8);
 
+/* Tensor-memory probes (cycles per round of 64 doubles per thread read back from TMEM, 4 CTAs of
+ * 128 threads per SM): [0] DFMA only, [1] tcgen05.ld only, [2] ld + 8 DFMA per 8 doubles,
+ * [3] ld + 16 DFMA, [4] as 1, [5] ld issued one chunk ahead + 16 DFMA, [6] one warp alone,
+ * [7] read-back mismatches (must be 0), [8..13] CTAs co-resident with CTA 0 in probes 0..5,
+ * [14] occupancy the runtime reports.  Used to decide whether TMEM can hold the time-invariant
+ * coefficient arrays of the march.  out[16]. */
+int kw_fd1d_tmem_probe(int32_t device, double* out16);
+
+/* DFMA throughput (TFLOP/s) against the number of distinct REGISTER source operands:
+ * out[0..3] with 16 warps per SM: one register source, two, three distinct, three with one shared by
+ * consecutive instructions; out[4..7] the same with 64 warps per SM.  The march's DFMAs all read three
+ * registers, so this -- not the one-register figure of kw_fd1d_fp64_peak -- is its practical ceiling. */
+int kw_fd1d_dfma_probe(int32_t device, double* out8);
+
 const char* kw_fd1d_version(void);
 
 #ifdef __cplusplus

@@ -26,17 +26,35 @@ namespace {
 // ---------------------------------------------------------------- variants of Layout B
 typedef void (*RegKernel)(const Fd1dBatch);
 struct RegVariant {
-    int id;        // 100*log2(P/32) + serial; see the table
+    int id;        // 100*log2(P/32) + serial (+1000 for the fp32 march); see the table
+    int prec;      // KW_FD1D_F64 / KW_FD1D_F32
     int M, P, minb;
     bool proj_smem, dq_smem;
     RegKernel fn;
     size_t smem;
+    int tmem_cols;  // tensor-memory columns each CTA allocates (0 = none)
 };
 
 #define KW_VARIANT(ID, M_, P_, MINB_, PJ_, DQ_)                                                   \
     {                                                                                              \
-        ID, M_, P_, MINB_, PJ_, DQ_, fd1d_reg_kernel<M_, P_, MINB_, PJ_, DQ_>,                     \
+        ID, KW_FD1D_F64, M_, P_, MINB_, PJ_, DQ_, fd1d_reg_kernel<double, M_, P_, MINB_, PJ_, DQ_>,  \
             RegSmem<M_, P_>::bytes(PJ_, DQ_)                                                       \
+    }
+#define KW_VARIANT_I(ID, M_, P_, MINB_, PJ_, DQ_)                                                 \
+    {                                                                                              \
+        ID, KW_FD1D_F64, M_, P_, MINB_, PJ_, DQ_, fd1d_reg_kernel<double, M_, P_, MINB_, PJ_, DQ_, true>, \
+            RegSmem<M_, P_>::bytes(PJ_, DQ_)                                                       \
+    }
+
+#define KW_VARIANT_T(ID, MINB_, ICMP_)                                                            \
+    {                                                                                              \
+        ID, KW_FD1D_F64, 8, 128, MINB_, false, false, fd1d_reg_kernel<double, 8, 128, MINB_, false, false, ICMP_, true>, \
+            RegSmem<8, 128>::bytes(false, false), 128                                              \
+    }
+#define KW_VARIANT_F32(ID, M_, P_, MINB_)                                                         \
+    {                                                                                              \
+        ID, KW_FD1D_F32, M_, P_, MINB_, false, false, fd1d_reg_kernel<float, M_, P_, MINB_, false, false>, \
+            RegSmem<M_, P_>::bytes(false, false)                                                   \
     }
 
 // the first entry of each P is the default of the per-xDim dispatch
@@ -51,31 +69,42 @@ const RegVariant g_variants[] = {
     KW_VARIANT(203, 8, 128, 4, true, true),
     KW_VARIANT(204, 8, 128, 4, true, false),
     KW_VARIANT(205, 8, 128, 3, true, true),
+    KW_VARIANT_I(211, 8, 128, 3, false, false),  // 201 with the projection compare on the integer pipe
+    KW_VARIANT_I(213, 8, 128, 4, true, true),
+    KW_VARIANT_T(221, 4, false),  // coefficient arrays in tensor memory, 4 PDEs per SM
+    KW_VARIANT_T(222, 4, true),
     KW_VARIANT(301, 8, 256, 1, false, false),  // x <= 2048
     KW_VARIANT(302, 8, 256, 2, true, true),
     KW_VARIANT(401, 8, 512, 1, true, true),    // x <= 4096
     KW_VARIANT(402, 8, 512, 1, true, false),
+    // fp32 march (fp64 set-up): FD1D.GPU.PRECISION = f32
+    KW_VARIANT_F32(1001, 8, 32, 16),
+    KW_VARIANT_F32(1101, 8, 64, 8),
+    KW_VARIANT_F32(1201, 8, 128, 4),
+    KW_VARIANT_F32(1301, 8, 256, 2),
+    KW_VARIANT_F32(1401, 8, 512, 1),
 };
 constexpr int kNumVariants = sizeof(g_variants) / sizeof(g_variants[0]);
 constexpr int kMaxRegX = 4096;
 
-const RegVariant* find_variant(int xDim, int want_id)
+const RegVariant* find_variant(int xDim, int want_id, int prec)
 {
     const RegVariant* first_fit = nullptr;
     for (int i = 0; i < kNumVariants; ++i) {
         const RegVariant& v = g_variants[i];
-        if (v.M * v.P < xDim) continue;
+        if (v.M * v.P < xDim || v.prec != prec) continue;
         if (!first_fit || v.P < first_fit->P) first_fit = &v;
     }
     if (!first_fit) return nullptr;
     if (want_id > 0) {
         for (int i = 0; i < kNumVariants; ++i)
-            if (g_variants[i].id == want_id && g_variants[i].M * g_variants[i].P >= xDim) return &g_variants[i];
+            if (g_variants[i].id == want_id && g_variants[i].prec == prec && g_variants[i].M * g_variants[i].P >= xDim)
+                return &g_variants[i];
         return nullptr;
     }
     // auto: the first entry of the smallest fitting P (the table lists the default first)
     for (int i = 0; i < kNumVariants; ++i)
-        if (g_variants[i].P == first_fit->P) return &g_variants[i];
+        if (g_variants[i].P == first_fit->P && g_variants[i].prec == prec) return &g_variants[i];
     return first_fit;
 }
 
@@ -410,8 +439,8 @@ int kw_fd1d_create(const kw_fd1d_config* cfg, kw_fd1d_handle** out)
         return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::init: FD1D.DENSITY and FD1D.SCALE must be positive");
     if (cfg->exact < 0 || cfg->exact > 2)
         return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::init: FD1D.GPU.EXACT must be 0, 1 or 2");
-    if (cfg->precision != KW_FD1D_F64)
-        return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::init: only FD1D.GPU.PRECISION = f64 is built in this round");
+    if (cfg->precision != KW_FD1D_F64 && cfg->precision != KW_FD1D_F32)
+        return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::init: FD1D.GPU.PRECISION must be f64 or f32");
 
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -434,7 +463,7 @@ int kw_fd1d_create(const kw_fd1d_config* cfg, kw_fd1d_handle** out)
     int layout = cfg->layout;
     if (layout == KW_FD1D_LAYOUT_AUTO) layout = cfg->x_grid_size <= kMaxRegX ? KW_FD1D_LAYOUT_REG : KW_FD1D_LAYOUT_SOA;
     if (layout == KW_FD1D_LAYOUT_REG) {
-        h->var = find_variant((int)cfg->x_grid_size, cfg->variant);
+        h->var = find_variant((int)cfg->x_grid_size, cfg->variant, cfg->precision);
         if (!h->var)
             return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::init: no register-layout kernel variant for this FD1D.X_GRID_SIZE / FD1D.GPU.VARIANT");
         KW_CUDA(h, cudaFuncSetAttribute(h->var->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->var->smem));
@@ -444,8 +473,24 @@ int kw_fd1d_create(const kw_fd1d_config* cfg, kw_fd1d_handle** out)
         int occ = 0;
         KW_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->var->fn, h->var->P, h->var->smem));
         if (occ < 1) return fail(h, KW_FD1D_ECUDA, "Fd1dGpu_Pricer::init: kernel variant does not fit on an SM");
+        if (h->var->tmem_cols > 0) {
+            // The occupancy calculator answers 1 for any kernel that allocates tensor memory, but the
+            // hardware co-schedules CTAs as long as their tcgen05.alloc requests fit the SM's 512 columns
+            // (measured: kw_fd1d_tmem_probe finds 4 x 128 columns resident).  Size the persistent grid
+            // from the real limits: registers, shared memory, TMEM columns.
+            const int by_regs = 65536 / (fa.numRegs * h->var->P);
+            const int by_smem = (int)((size_t)prop.sharedMemPerMultiprocessor / (h->var->smem + 1024));
+            const int by_tmem = 512 / h->var->tmem_cols;
+            occ = std::max(1, std::min({by_regs, by_smem, by_tmem, h->var->minb}));
+            // ... and ask for the shared-memory carve-out that many CTAs need (the driver would size it
+            // for the single CTA the calculator believes in)
+            KW_CUDA(h, cudaFuncSetAttribute(h->var->fn, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                            cudaSharedmemCarveoutMaxShared));
+        }
         h->ctas_per_sm = occ;
     } else if (layout == KW_FD1D_LAYOUT_SOA) {
+        if (cfg->precision != KW_FD1D_F64)
+            return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::init: the SoA layout (FD1D.GPU.LAYOUT = soa) is fp64 only");
         cudaFuncAttributes fa;
         KW_CUDA(h, cudaFuncGetAttributes(&fa, fd1d_soa_march_kernel));
         h->regs = fa.numRegs;
@@ -629,6 +674,104 @@ int kw_fd1d_microbench(int32_t device, double* out8)
     cudaError_t e = cudaMemcpy(out8, d, 8 * sizeof(double), cudaMemcpyDeviceToHost);
     cudaFree(d);
     return e == cudaSuccess ? KW_FD1D_OK : KW_FD1D_ECUDA;
+}
+
+
+int kw_fd1d_tmem_probe(int32_t device, double* out16)
+{
+    if (!out16) return KW_FD1D_EINVAL;
+    if (cudaSetDevice(device) != cudaSuccess) return KW_FD1D_ECUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return KW_FD1D_ECUDA;
+    const int grid = prop.multiProcessorCount * 4;
+    const size_t nrec = 3 + 3 * (size_t)grid;
+    double* d = nullptr;
+    long long* cyc = nullptr;
+    if (cudaMalloc(&d, 64) != cudaSuccess || cudaMalloc(&cyc, nrec * 8) != cudaSuccess) return KW_FD1D_ECUDA;
+    typedef void (*Probe)(double*, long long*, int, double);
+    const Probe probes[6] = {tmem_probe_kernel<0>, tmem_probe_kernel<1>, tmem_probe_kernel<2>,
+                             tmem_probe_kernel<3>, tmem_probe_kernel<4>, tmem_probe_kernel<5>};
+    const int iters = 2000;
+    double mism = 0.;
+    std::vector<long long> hc(nrec);
+    for (int i = 0; i < 16; ++i) out16[i] = 0.;
+    for (int m = 0; m < 7; ++m) {
+        cudaMemset(cyc, 0, nrec * 8);
+        if (m < 6)
+            probes[m]<<<grid, 128>>>(d, cyc, iters, 1.0);
+        else
+            probes[1]<<<1, 32>>>(d, cyc, iters, 1.0);  // one warp alone: ld + wait round trip
+        if (cudaMemcpy(hc.data(), cyc, nrec * 8, cudaMemcpyDeviceToHost) != cudaSuccess) {
+            cudaFree(d);
+            cudaFree(cyc);
+            return KW_FD1D_ECUDA;
+        }
+        out16[m] = (double)hc[0] / iters;  // cycles per round of 8 chunks
+        mism += (double)hc[1];
+        if (m < 6) {
+            // how many CTAs shared CTA 0's SM for at least half of its timed loop
+            const long long sm0 = hc[2], a0 = hc[3], a1 = hc[4];
+            int co = 0;
+            for (int b = 0; b < grid; ++b) {
+                if (hc[2 + 3 * b] != sm0) continue;
+                const long long lo = std::max(a0, hc[3 + 3 * b]), hi = std::min(a1, hc[4 + 3 * b]);
+                if (hi - lo > (a1 - a0) / 2) ++co;
+            }
+            out16[8 + m] = co;
+            if (getenv("KW_PROBE_DEBUG")) {
+                for (int b = 0; b < grid; ++b)
+                    if (hc[2 + 3 * b] == sm0)
+                        fprintf(stderr, "probe %d: sm %lld cta %d start %+lld dur %lld\n", m, sm0, b,
+                                hc[3 + 3 * b] - a0, hc[4 + 3 * b] - hc[3 + 3 * b]);
+            }
+            if (m == 0 && hc[2 + 3 * grid] > 0) out16[15] = (double)hc[0] / (double)hc[2 + 3 * grid];  // clock64 ticks per ns
+        }
+    }
+    out16[7] = mism;
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tmem_probe_kernel<3>, 128, 0);
+    out16[14] = occ;
+    cudaFree(d);
+    cudaFree(cyc);
+    return KW_FD1D_OK;
+}
+
+int kw_fd1d_dfma_probe(int32_t device, double* out8)
+{
+    if (!out8) return KW_FD1D_EINVAL;
+    if (cudaSetDevice(device) != cudaSuccess) return KW_FD1D_ECUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return KW_FD1D_ECUDA;
+    double *din = nullptr, *dout = nullptr;
+    if (cudaMalloc(&din, 64 * 8) != cudaSuccess || cudaMalloc(&dout, 64) != cudaSuccess) return KW_FD1D_ECUDA;
+    double hin[64];
+    for (int i = 0; i < 64; ++i) hin[i] = 1e-3 * (i + 1);
+    cudaMemcpy(din, hin, sizeof hin, cudaMemcpyHostToDevice);
+    typedef void (*K)(const double*, double*, int);
+    const K ks[4] = {dfma_operand_kernel<1>, dfma_operand_kernel<2>, dfma_operand_kernel<3>, dfma_operand_kernel<4>};
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int iters = 4096;
+    for (int occ = 0; occ < 2; ++occ) {             // 16 and 64 warps per SM
+        const int ctas = occ == 0 ? 4 : 16;
+        const int grid = prop.multiProcessorCount * ctas;
+        for (int k = 0; k < 4; ++k) {
+            ks[k]<<<grid, 128>>>(din, dout, 64);
+            cudaEventRecord(e0);
+            ks[k]<<<grid, 128>>>(din, dout, iters);
+            cudaEventRecord(e1);
+            if (cudaEventSynchronize(e1) != cudaSuccess) return KW_FD1D_ECUDA;
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            out8[occ * 4 + k] = 2.0 * 32.0 * iters * (double)grid * 128 / (ms * 1e-3) * 1e-12;  // TFLOP/s
+        }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(din);
+    cudaFree(dout);
+    return KW_FD1D_OK;
 }
 
 const char* kw_fd1d_version(void) { return "kwinto-b200 fd1d 0.1 (sm_100a)"; }

@@ -27,6 +27,7 @@
 #include <type_traits>
 
 #include "fd1d_common.cuh"
+#include "tmem.cuh"
 
 namespace kwfd1d {
 
@@ -102,16 +103,86 @@ __device__ __forceinline__ void sts_f64(uint32_t a, double v)
     asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
 }
 
+// march-type-generic shared accesses: the exchange slots keep their 8-byte stride for float too
+template <class F>
+struct Pair {
+    F x, y;
+};
+template <class F>
+__device__ __forceinline__ Pair<F> make_pair_t(F x, F y)
+{
+    Pair<F> p;
+    p.x = x;
+    p.y = y;
+    return p;
+}
+template <class F>
+__device__ __forceinline__ F lds_t(uint32_t a);
+template <>
+__device__ __forceinline__ double lds_t<double>(uint32_t a)
+{
+    return lds_f64(a);
+}
+template <>
+__device__ __forceinline__ float lds_t<float>(uint32_t a)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_t_impl(uint32_t a, double v) { sts_f64(a, v); }
+__device__ __forceinline__ void sts_t_impl(uint32_t a, float v)
+{
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+template <class F>
+__device__ __forceinline__ void sts_t(uint32_t a, F v)
+{
+    sts_t_impl(a, v);
+}
+template <class F>
+__device__ __forceinline__ Pair<F> lds_pair(uint32_t a)
+{
+    const double2 d = lds_v2f64(a);
+    return make_pair_t<F>((F)d.x, (F)d.y);
+}
+
 // std::max(v, payoff) of the reference (src/Math/kwFd1d.cpp:131): (a < b) ? b : a.
 // One DSETP + two selects; fmax() would add NaN canonicalisation the scheme does not need.
-__device__ __forceinline__ double max_like_std(double a, double b) { return (a < b) ? b : a; }
+template <class F>
+__device__ __forceinline__ F max_like_std(F a, F b)
+{
+    return (a < b) ? b : a;
+}
+// The same selection with the comparison on the integer pipe: for b >= +0 the order of the bit
+// patterns as signed 64-bit integers is the order of the doubles (every negative a, and -0, sorts
+// below +0; NaNs do not occur).  "Never project" is the floor -0.0 = INT64_MIN.  The only
+// difference from the DSETP form: a = -0.0 against b = +0.0 yields +0.0, the same number.
+__device__ __forceinline__ double max_like_icmp(double a, double b)
+{
+    return (__double_as_longlong(a) < __double_as_longlong(b)) ? b : a;
+}
+__device__ __forceinline__ float max_like_icmp(float a, float b)
+{
+    return (__float_as_int(a) < __float_as_int(b)) ? b : a;
+}
 
 // PROJ_SMEM / DQ_SMEM: keep the projection floor / the D*Q fix-up array in shared memory
 // instead of registers (fewer registers -> more CTAs per SM, more shared-memory wavefronts).
-template <int M, int P, int MINB, bool PROJ_SMEM, bool DQ_SMEM>
+// F: the arithmetic type of the time march.  double = the parity path (1e-9 absolute); float =
+// FD1D.GPU.PRECISION f32: the whole set-up (grid, payoff, B rows, pivots, spikes, scan multipliers)
+// stays in fp64 and only the march runs in fp32 (an all-fp32 set-up misses the 1e-4 bar).
+// TMEM: the coefficient arrays g~, D, a~, D*R, D*Q and the payoff floor live in tensor memory
+// (tmem.cuh) instead of registers and are streamed back with tcgen05.ld just before use: 128 instead
+// of 168 registers per thread, i.e. 4 instead of 3 resident PDEs per SM, without touching the
+// shared-memory pipe that the scans' shuffles already keep busy.
+template <class F, int M, int P, int MINB, bool PROJ_SMEM, bool DQ_SMEM, bool ICMP = false, bool TMEM = false>
 __global__ void __launch_bounds__(P, MINB) fd1d_reg_kernel(const Fd1dBatch B)
 {
+    static_assert(!TMEM || (std::is_same<F, double>::value && M == 8 && P == 128 && !PROJ_SMEM && !DQ_SMEM),
+                  "TMEM variant: fp64, 8 nodes per thread, one warp per TMEM lane quarter");
     static_assert(M % 2 == 0 && P % 32 == 0, "M even, whole warps");
+    static_assert(std::is_same<F, double>::value || (!PROJ_SMEM && !DQ_SMEM), "fp32 march keeps everything in registers");
     using L = RegSmem<M, P>;
     constexpr int N = L::N;
     constexpr int NW = L::NW;
@@ -149,6 +220,17 @@ __global__ void __launch_bounds__(P, MINB) fd1d_reg_kernel(const Fd1dBatch B)
     const int xDim = B.xDim;
     const int nsteps = B.tDim - 1;
 
+    // tensor memory: 128 columns per CTA = 64 doubles per thread (48 used), freed at kernel exit
+    uint32_t tbase = 0;
+    if constexpr (TMEM) {
+        __shared__ uint32_t s_taddr;
+        if (warp == 0) tmem::alloc128(smem_addr(&s_taddr));
+        tmem::fence_before();
+        __syncthreads();
+        tmem::fence_after();
+        tbase = s_taddr + ((uint32_t)(warp & 3) << 21);  // lane field (bits 31:16) = 32 * (warp % 4)
+    }
+
     for (uint32_t pde = blockIdx.x; pde < B.n_pde; pde += gridDim.x) {
         const uint32_t rep = B.pde_rep ? __ldg(B.pde_rep + pde) : pde;
         const kw_option opt = load_option(B.opts + rep);
@@ -165,7 +247,7 @@ __global__ void __launch_bounds__(P, MINB) fd1d_reg_kernel(const Fd1dBatch B)
             if (j < xDim) p = payoff_node(sc.put, x);
             v[i] = p;
             // projection skips the last node (src/Math/kwFd1d.cpp:130); European: never
-            pj[i] = (sc.american && j < xDim - 1) ? p : -CUDART_INF;
+            pj[i] = (sc.american && j < xDim - 1) ? p : (ICMP ? -0. : -CUDART_INF);
         }
         if (PROJ_SMEM) {
 #pragma unroll
@@ -372,7 +454,9 @@ __global__ void __launch_bounds__(P, MINB) fd1d_reg_kernel(const Fd1dBatch B)
             bmax = scr[0];
 #pragma unroll
             for (int w = 1; w < NW; ++w) bmax = fmax(bmax, scr[w]);
-            const double tol = 0x1p-56 / (bmax * (double)B.tDim);
+            // fp32 march: anything below 2^-30 of the local scale over the whole march is far inside its
+            // own rounding (2^-24 per operation)
+            const double tol = (std::is_same<F, double>::value ? 0x1p-56 : 0x1p-30) / (bmax * (double)B.tDim);
             const int j_src = min((warp + 1) * 32 * M + M - 1, xDim - 1);
             const double growth =
                 sc.put ? 1. : exp(fmax(0., xs[j_src]) - fmax(0., xs[min(k * M, xDim - 1)]));
@@ -443,25 +527,188 @@ __global__ void __launch_bounds__(P, MINB) fd1d_reg_kernel(const Fd1dBatch B)
         const uint32_t a_zx = smem_addr(zx);
         const uint32_t a_rows = smem_addr(t_cf + warp * NWP);
 
+        // march-typed copies (identity for the fp64 march)
+        F vm[M], am[M], gm[M], Dm[M], DRm[M], DQm[M], pm[M], Afm[4], Gbm[4];
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+            vm[i] = (F)v[i];
+            am[i] = (F)a[i];
+            gm[i] = (F)g[i];
+            Dm[i] = (F)D[i];
+            DRm[i] = (F)DR[i];
+            DQm[i] = (F)DQ[i];
+            pm[i] = (F)pj[i];
+        }
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            Afm[d] = (F)Af[d];
+            Gbm[d] = (F)Gb[d];
+        }
+        const F PWexfm = (F)PWexf, PWbsm = (F)PWbs, R0nm = (F)R0n, Hsm = (F)Hs, G0m = (F)G0, H0nm = (F)H0n;
+
         // ---------------- time march: tDim-1 steps, one barrier each ----------------------
         auto march = [&](auto mode_c) {
             constexpr int MODE = decltype(mode_c)::value;
             constexpr int NLEV = MODE <= 1 ? 5 : 6 - MODE;  // scan levels kept
+            F af4 = F(0), gb4 = F(0);
+            if (NLEV == 5) {
+                af4 = (F)s_af4[k];
+                gb4 = (F)s_gb4[k];
+            }
+            // local forward sweep from 0 for the first step (later ones are fused into the loop tail)
+            F y[M];
+            y[0] = vm[0];
+#pragma unroll
+            for (int i = 1; i < M; ++i) y[i] = fma(am[i], y[i - 1], vm[i]);
+            // software pipeline: the level-0 shuffle of the forward scan is issued at the END of the
+            // previous iteration, so the local backward sweep runs in its shadow
+            F o0 = __shfl_up_sync(FULL, y[M - 1], 1);
+            for (int step = 0; step < nsteps; ++step) {
+                // inclusive forward scan of the chunk-end values inside the warp
+                F S = fma(Afm[0], o0, y[M - 1]);
+#pragma unroll
+                for (int d = 1; d < 4; ++d) {
+                    if (d < NLEV) {
+                        const F o = __shfl_up_sync(FULL, S, 1 << d);
+                        S = fma(Afm[d], o, S);
+                    }
+                }
+                if (NLEV == 5) {
+                    const F o = __shfl_up_sync(FULL, S, 16);
+                    S = fma(af4, o, S);
+                }
+                // local backward sweep of the local forward result; r_i = D_i ul_i - v_i on the fly
+#pragma unroll
+                for (int i = M - 2; i >= 0; --i) y[i] = fma(gm[i], y[i + 1], y[i]);
+#pragma unroll
+                for (int i = 0; i < M; ++i) vm[i] = fma(Dm[i], y[i], -vm[i]);
+                // shifted backward scan: lane k holds chunk k+1
+                const F uln = __shfl_down_sync(FULL, y[0], 1);
+                F T = fma(R0nm, S, lane < 31 ? uln : F(0));
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    if (d < NLEV) {
+                        const F o = __shfl_down_sync(FULL, T, 1 << d);
+                        T = fma(Gbm[d], o, T);
+                    }
+                }
+                if (NLEV == 5) {
+                    const F o = __shfl_down_sync(FULL, T, 16);
+                    T = fma(gb4, o, T);
+                }
+                F Sm1 = __shfl_up_sync(FULL, S, 1);
+                if (lane == 0) Sm1 = F(0);
+
+                F Xw = F(0), Xbw = F(0);
+                if (NW > 1) {
+                    // every lane stores (no divergent branch); only lanes 0 and 31 are read back
+                    const uint32_t par = (uint32_t)(step & 1) * (ZS * 8);
+                    sts_t<F>(a_mine + par, lane == 0 ? fma(G0m, T, y[0]) : S);
+                    __syncthreads();
+                    const uint32_t zrow = a_zx + par + (uint32_t)warp * 256;  // slot row of warp - 1
+                    if (MODE == 0) {
+#pragma unroll
+                        for (int w = 0; w < NW; ++w) {
+                            const F f = lds_t<F>(a_zx + par + (w + 1) * 256 + 31 * 8);
+                            const F b = lds_t<F>(a_zx + par + (w + 1) * 256);
+                            const F cf = (F)lds_f64(a_rows + w * 8);
+                            const F cb = (F)lds_f64(a_rows + (NW * NWP + w) * 8);
+                            const F ce = (F)lds_f64(a_rows + (2 * NW * NWP + w) * 8);
+                            Xw = fma(cf, f, Xw);
+                            Xbw = fma(cb, b, Xbw);
+                            Xbw = fma(ce, f, Xbw);
+                        }
+                    } else {
+                        // nearest-warp carries only: X_w = zf[w-1]; Xb_w = zb[w+1] + H0[w+1] * zf[w]
+                        const F fm1 = lds_t<F>(zrow + 31 * 8);
+                        const F fw = lds_t<F>(zrow + 256 + 31 * 8);
+                        const F bp1 = lds_t<F>(zrow + 512);
+                        Xw = fm1;
+                        Xbw = fma(H0nm, fw, bp1);
+                    }
+                }
+                const F Yin = fma(PWexfm, Xw, Sm1);
+                const F Uin = fma(PWbsm, Xbw, fma(Hsm, Xw, T));
+                // fix-up + projection, fused with the NEXT step's local forward sweep so that the
+                // sweep's dependent chain hides behind the independent per-node fix-ups
+#pragma unroll
+                for (int c = 0; c < M2; ++c) {
+                    Pair<F> pp, qq;
+                    if (PROJ_SMEM)
+                        pp = lds_pair<F>(a_proj + c * (P * 16));
+                    else
+                        pp = make_pair_t<F>(pm[2 * c], pm[2 * c + 1]);
+                    if (DQ_SMEM)
+                        qq = lds_pair<F>(a_dq + c * (P * 16));
+                    else
+                        qq = make_pair_t<F>(DQm[2 * c], DQm[2 * c + 1]);
+                    {
+                        const int i = 2 * c;
+                        F r = fma(DRm[i], Yin, vm[i]);
+                        r = fma(qq.x, Uin, r);
+                        vm[i] = ICMP ? max_like_icmp(r, pp.x) : max_like_std(r, pp.x);
+                        y[i] = i ? fma(am[i], y[i - 1], vm[i]) : vm[i];
+                    }
+                    {
+                        const int i = 2 * c + 1;
+                        F r = fma(DRm[i], Yin, vm[i]);
+                        r = fma(qq.y, Uin, r);
+                        vm[i] = ICMP ? max_like_icmp(r, pp.y) : max_like_std(r, pp.y);
+                        y[i] = fma(am[i], y[i - 1], vm[i]);
+                    }
+                }
+                o0 = __shfl_up_sync(FULL, y[M - 1], 1);
+            }
+        };
+        // ---------------- TMEM variant of the march ----------------------------------------
+        // columns (2 per double): [0,16) g~[0..7] | [16,32) D[0..7] | [32+16c, 48+16c) node pair c:
+        // a~[2c], a~[2c+1], DR[2c], DR[2c+1], DQ[2c], DQ[2c+1], p[2c], p[2c+1]
+        if constexpr (TMEM) {
+            double t8[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t8[i] = g[i];
+            tmem::st8(tbase, t8);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t8[i] = D[i];
+            tmem::st8(tbase + 16, t8);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                t8[0] = a[2 * c];
+                t8[1] = a[2 * c + 1];
+                t8[2] = DR[2 * c];
+                t8[3] = DR[2 * c + 1];
+                t8[4] = DQ[2 * c];
+                t8[5] = DQ[2 * c + 1];
+                t8[6] = pj[2 * c];
+                t8[7] = pj[2 * c + 1];
+                tmem::st8(tbase + 32 + 16 * c, t8);
+            }
+            tmem::wait_st();
+        }
+        auto march_tmem = [&](auto mode_c) {
+            constexpr int MODE = decltype(mode_c)::value;
+            constexpr int NLEV = MODE <= 1 ? 5 : 6 - MODE;
             double af4 = 0., gb4 = 0.;
             if (NLEV == 5) {
                 af4 = s_af4[k];
                 gb4 = s_gb4[k];
             }
-            // local forward sweep from 0 for the first step (later ones are fused into the loop tail)
-            double y[M];
-            y[0] = v[0];
+            double w[M], y[M];
 #pragma unroll
-            for (int i = 1; i < M; ++i) y[i] = fma(a[i], y[i - 1], v[i]);
-            // software pipeline: the level-0 shuffle of the forward scan is issued at the END of the
-            // previous iteration, so the local backward sweep runs in its shadow
+            for (int i = 0; i < M; ++i) w[i] = v[i];
+            // first local forward sweep: the a~ come from the pair blocks
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                double q[8];
+                tmem::ld8(tbase + 32 + 16 * c, q);
+                tmem::wait_ld_dep(q);
+                y[2 * c] = c ? fma(q[0], y[2 * c - 1], w[2 * c]) : w[0];
+                y[2 * c + 1] = fma(q[1], y[2 * c], w[2 * c + 1]);
+            }
             double o0 = __shfl_up_sync(FULL, y[M - 1], 1);
+            double g8[8];
+            tmem::ld8(tbase, g8);
             for (int step = 0; step < nsteps; ++step) {
-                // inclusive forward scan of the chunk-end values inside the warp
                 double S = fma(Af[0], o0, y[M - 1]);
 #pragma unroll
                 for (int d = 1; d < 4; ++d) {
@@ -474,12 +721,16 @@ __global__ void __launch_bounds__(P, MINB) fd1d_reg_kernel(const Fd1dBatch B)
                     const double o = __shfl_up_sync(FULL, S, 16);
                     S = fma(af4, o, S);
                 }
-                // local backward sweep of the local forward result; r_i = D_i ul_i - v_i on the fly
+                tmem::wait_ld_dep(g8);
+                double d8[8];
+                tmem::ld8(tbase + 16, d8);
 #pragma unroll
-                for (int i = M - 2; i >= 0; --i) y[i] = fma(g[i], y[i + 1], y[i]);
+                for (int i = M - 2; i >= 0; --i) y[i] = fma(g8[i], y[i + 1], y[i]);
+                tmem::wait_ld_dep(d8);
 #pragma unroll
-                for (int i = 0; i < M; ++i) v[i] = fma(D[i], y[i], -v[i]);
-                // shifted backward scan: lane k holds chunk k+1
+                for (int i = 0; i < M; ++i) w[i] = fma(d8[i], y[i], -w[i]);
+                double q[4][8];
+                tmem::ld8(tbase + 32, q[0]);
                 const double uln = __shfl_down_sync(FULL, y[0], 1);
                 double T = fma(R0n, S, lane < 31 ? uln : 0.);
 #pragma unroll
@@ -495,28 +746,25 @@ __global__ void __launch_bounds__(P, MINB) fd1d_reg_kernel(const Fd1dBatch B)
                 }
                 double Sm1 = __shfl_up_sync(FULL, S, 1);
                 if (lane == 0) Sm1 = 0.;
-
                 double Xw = 0., Xbw = 0.;
-                if (NW > 1) {
-                    // every lane stores (no divergent branch); only lanes 0 and 31 are read back
+                {
                     const uint32_t par = (uint32_t)(step & 1) * (ZS * 8);
                     sts_f64(a_mine + par, lane == 0 ? fma(G0, T, y[0]) : S);
                     __syncthreads();
-                    const uint32_t zrow = a_zx + par + (uint32_t)warp * 256;  // slot row of warp - 1
+                    const uint32_t zrow = a_zx + par + (uint32_t)warp * 256;
                     if (MODE == 0) {
 #pragma unroll
-                        for (int w = 0; w < NW; ++w) {
-                            const double f = lds_f64(a_zx + par + (w + 1) * 256 + 31 * 8);
-                            const double b = lds_f64(a_zx + par + (w + 1) * 256);
-                            const double cf = lds_f64(a_rows + w * 8);
-                            const double cb = lds_f64(a_rows + (NW * NWP + w) * 8);
-                            const double ce = lds_f64(a_rows + (2 * NW * NWP + w) * 8);
+                        for (int ww = 0; ww < NW; ++ww) {
+                            const double f = lds_f64(a_zx + par + (ww + 1) * 256 + 31 * 8);
+                            const double b = lds_f64(a_zx + par + (ww + 1) * 256);
+                            const double cf = lds_f64(a_rows + ww * 8);
+                            const double cb = lds_f64(a_rows + (NW * NWP + ww) * 8);
+                            const double ce = lds_f64(a_rows + (2 * NW * NWP + ww) * 8);
                             Xw = fma(cf, f, Xw);
                             Xbw = fma(cb, b, Xbw);
                             Xbw = fma(ce, f, Xbw);
                         }
                     } else {
-                        // nearest-warp carries only: X_w = zf[w-1]; Xb_w = zb[w+1] + H0[w+1] * zf[w]
                         const double fm1 = lds_f64(zrow + 31 * 8);
                         const double fw = lds_f64(zrow + 256 + 31 * 8);
                         const double bp1 = lds_f64(zrow + 512);
@@ -526,50 +774,57 @@ __global__ void __launch_bounds__(P, MINB) fd1d_reg_kernel(const Fd1dBatch B)
                 }
                 const double Yin = fma(PWexf, Xw, Sm1);
                 const double Uin = fma(PWbs, Xbw, fma(Hs, Xw, T));
-                // fix-up + projection, fused with the NEXT step's local forward sweep so that the
-                // sweep's dependent chain hides behind the independent per-node fix-ups
 #pragma unroll
-                for (int c = 0; c < M2; ++c) {
-                    double2 pp, qq;
-                    if (PROJ_SMEM)
-                        pp = lds_v2f64(a_proj + c * (P * 16));
+                for (int c = 0; c < 4; ++c) {
+                    tmem::wait_ld_dep(q[c]);
+                    if (c < 3)
+                        tmem::ld8(tbase + 32 + 16 * (c + 1), q[c + 1]);
                     else
-                        pp = make_double2(pj[2 * c], pj[2 * c + 1]);
-                    if (DQ_SMEM)
-                        qq = lds_v2f64(a_dq + c * (P * 16));
-                    else
-                        qq = make_double2(DQ[2 * c], DQ[2 * c + 1]);
+                        tmem::ld8(tbase, g8);  // next step's g~
                     {
                         const int i = 2 * c;
-                        double r = fma(DR[i], Yin, v[i]);
-                        r = fma(qq.x, Uin, r);
-                        v[i] = max_like_std(r, pp.x);
-                        y[i] = i ? fma(a[i], y[i - 1], v[i]) : v[i];
+                        double r = fma(q[c][2], Yin, w[i]);
+                        r = fma(q[c][4], Uin, r);
+                        w[i] = ICMP ? max_like_icmp(r, q[c][6]) : max_like_std(r, q[c][6]);
+                        y[i] = i ? fma(q[c][0], y[i - 1], w[i]) : w[i];
                     }
                     {
                         const int i = 2 * c + 1;
-                        double r = fma(DR[i], Yin, v[i]);
-                        r = fma(qq.y, Uin, r);
-                        v[i] = max_like_std(r, pp.y);
-                        y[i] = fma(a[i], y[i - 1], v[i]);
+                        double r = fma(q[c][3], Yin, w[i]);
+                        r = fma(q[c][5], Uin, r);
+                        w[i] = ICMP ? max_like_icmp(r, q[c][7]) : max_like_std(r, q[c][7]);
+                        y[i] = fma(q[c][1], y[i - 1], w[i]);
                     }
                 }
                 o0 = __shfl_up_sync(FULL, y[M - 1], 1);
             }
+            tmem::wait_ld_dep(g8);  // nothing in flight when the next PDE overwrites the arrays
+#pragma unroll
+            for (int i = 0; i < M; ++i) vm[i] = w[i];
         };
-        switch (mode) {
-            case 0: march(std::integral_constant<int, 0>{}); break;
-            case 1: march(std::integral_constant<int, 1>{}); break;
-            case 2: march(std::integral_constant<int, 2>{}); break;
-            case 3: march(std::integral_constant<int, 3>{}); break;
-            default: march(std::integral_constant<int, 4>{}); break;
+        if constexpr (TMEM) {
+            switch (mode) {
+                case 0: march_tmem(std::integral_constant<int, 0>{}); break;
+                case 1: march_tmem(std::integral_constant<int, 1>{}); break;
+                case 2: march_tmem(std::integral_constant<int, 2>{}); break;
+                case 3: march_tmem(std::integral_constant<int, 3>{}); break;
+                default: march_tmem(std::integral_constant<int, 4>{}); break;
+            }
+        } else {
+            switch (mode) {
+                case 0: march(std::integral_constant<int, 0>{}); break;
+                case 1: march(std::integral_constant<int, 1>{}); break;
+                case 2: march(std::integral_constant<int, 2>{}); break;
+                case 3: march(std::integral_constant<int, 3>{}); break;
+                default: march(std::integral_constant<int, 4>{}); break;
+            }
         }
         if (k == 0) atomicAdd(&B.status[2 + mode], 1u);
 
         // ---------------- epilogue: interpolate every option of this chain -----------------
         __syncthreads();
 #pragma unroll
-        for (int i = 0; i < M; ++i) scr[k * M + i] = v[i];
+        for (int i = 0; i < M; ++i) scr[k * M + i] = (double)vm[i];
         __syncthreads();
         {
             const uint32_t q0 = B.csr_start ? __ldg(B.csr_start + pde) : pde;
@@ -580,6 +835,11 @@ __global__ void __launch_bounds__(P, MINB) fd1d_reg_kernel(const Fd1dBatch B)
             }
         }
         __syncthreads();
+    }
+    if constexpr (TMEM) {
+        tmem::fence_before();
+        __syncthreads();
+        if (warp == 0) tmem::dealloc128(tbase & 0xffffu);
     }
 }
 

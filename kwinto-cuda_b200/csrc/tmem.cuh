@@ -1,0 +1,77 @@
+// tmem.cuh -- Blackwell tensor memory (TMEM) used as a per-thread constant store.
+//
+// TMEM is 512 columns x 128 lanes x 32 bit per SM, reachable only through tcgen05.ld / tcgen05.st.
+// With the .32x32b shape lane l of the warp's lane quarter (32 * (warp % 4) + l) belongs to thread l,
+// so N columns are N private 32-bit words per thread: a second register file that costs no
+// registers and no shared-memory bandwidth.  The Fd1d march keeps time-invariant coefficient arrays
+// there (fd1d_reg.cuh, TMEM variants).  No tensor-core instruction is involved.
+// Measured on B200 (kw_fd1d_tmem_probe): 821 B/clk/SM read back by 16 warps with ld -> wait round
+// trips, ~21 cycles ld + wait for one warp alone; four CTAs x 128 columns co-reside on an SM.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace kwfd1d {
+namespace tmem {
+__device__ __forceinline__ void alloc128(uint32_t smem_slot_addr)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_slot_addr) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void dealloc128(uint32_t taddr)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(taddr) : "memory");
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// 8 doubles = 16 columns of this thread's lane
+__device__ __forceinline__ void ld8(uint32_t taddr, double (&d)[8])
+{
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = __hiloint2double((int)r[2 * i + 1], (int)r[2 * i]);
+}
+__device__ __forceinline__ void st8(uint32_t taddr, const double (&d)[8])
+{
+    uint32_t r[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        r[2 * i] = (uint32_t)__double2loint(d[i]);
+        r[2 * i + 1] = (uint32_t)__double2hiint(d[i]);
+    }
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};" ::"r"(r[0]),
+        "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(taddr)
+        : "memory");
+}
+// raw 16-register load; the xor of two of them keeps it alive without touching the FP64 pipe
+__device__ __forceinline__ uint32_t ld16_raw(uint32_t taddr)
+{
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    return r[0] ^ r[5] ^ r[10] ^ r[15];
+}
+// the wait, tied to the loaded values so that the compiler cannot consume them earlier
+__device__ __forceinline__ void wait_ld_dep(double (&d)[8])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+d"(d[0]), "+d"(d[1]), "+d"(d[2]), "+d"(d[3]), "+d"(d[4]), "+d"(d[5]), "+d"(d[6]), "+d"(d[7])::"memory");
+}
+}  // namespace tmem
+
+}  // namespace kwfd1d

@@ -81,6 +81,10 @@ def load_library(path: str = LIB_PATH):
     L.kw_fd1d_fp64_peak.restype = C.c_int
     L.kw_fd1d_microbench.argtypes = [C.c_int32, C.POINTER(C.c_double)]
     L.kw_fd1d_microbench.restype = C.c_int
+    L.kw_fd1d_tmem_probe.argtypes = [C.c_int32, C.POINTER(C.c_double)]
+    L.kw_fd1d_tmem_probe.restype = C.c_int
+    L.kw_fd1d_dfma_probe.argtypes = [C.c_int32, C.POINTER(C.c_double)]
+    L.kw_fd1d_dfma_probe.restype = C.c_int
     L.kw_fd1d_version.restype = C.c_char_p
     _lib = L
     return L
@@ -89,7 +93,7 @@ def load_library(path: str = LIB_PATH):
 EXPORTED_SYMBOLS = [  # every entry point include/kw_fd1d.h declares
     "kw_fd1d_config_default", "kw_fd1d_create", "kw_fd1d_destroy", "kw_fd1d_price", "kw_fd1d_price_device",
     "kw_fd1d_sync", "kw_fd1d_price_bs", "kw_fd1d_last_error", "kw_fd1d_get_info", "kw_fd1d_fp64_peak",
-    "kw_fd1d_microbench", "kw_fd1d_version",
+    "kw_fd1d_microbench", "kw_fd1d_tmem_probe", "kw_fd1d_dfma_probe", "kw_fd1d_version",
 ]
 
 
@@ -277,3 +281,30 @@ def microbench(device: int = 0) -> dict:
         raise RuntimeError("kw_fd1d_microbench failed (no CUDA device?)")
     names = ["dfma_dep", "shfl64_dep", "shfl64_dfma_dep", "syncthreads_4warps", "lds_dep", "dadd_dmnmx_dep"]
     return {k: out[i] for i, k in enumerate(names)}
+
+
+def tmem_probe(device: int = 0) -> dict:
+    """Cycles per round (64 doubles per thread from TMEM, 16 warps per SM) of the tensor-memory probes."""
+    L = load_library()
+    out = (C.c_double * 16)()
+    rc = L.kw_fd1d_tmem_probe(device, out)
+    if rc != KW_FD1D_OK:
+        raise RuntimeError("kw_fd1d_tmem_probe failed (no CUDA device?)")
+    names = ["dfma16_only", "ld_only", "ld_dfma8", "ld_dfma16", "ld_only_b", "ld_ahead_dfma16", "one_warp_ld",
+             "mismatches"]
+    res = {k: out[i] for i, k in enumerate(names)}
+    res["coresident_ctas"] = [int(out[8 + i]) for i in range(6)]
+    res["occupancy"] = int(out[14])
+    res["clock64_ticks_per_ns"] = out[15]
+    res["tmem_bytes_per_clk_sm"] = res["coresident_ctas"][1] * 128 * 64 * 8 / out[1] if out[1] else None
+    return res
+
+
+def dfma_probe(device: int = 0) -> dict:
+    """DFMA TFLOP/s by number of distinct register source operands, at 16 and 64 warps per SM."""
+    L = load_library()
+    out = (C.c_double * 8)()
+    if L.kw_fd1d_dfma_probe(device, out) != KW_FD1D_OK:
+        raise RuntimeError("kw_fd1d_dfma_probe failed (no CUDA device?)")
+    names = ["1reg", "2reg", "3reg", "3reg_shared"]
+    return {f"{n}_{w}warps": out[i * 4 + j] for i, w in enumerate((16, 64)) for j, n in enumerate(names)}
