@@ -264,6 +264,7 @@ def main():
         step()
         torch.cuda.synchronize()
         kernel_ms.append(pricer.info()["last_kernel_ms"])
+    launches_per_step = pricer.info()["launches"]  # status reset + chain compression (4) + march
     got_dev = d_prices.cpu().numpy()
 
     # ---- end-to-end leg through the public host API: pinned host options in, host prices out
@@ -337,7 +338,7 @@ def main():
                     "ms_per_step": e2e_ms_max / e2e_steps,
                     "api": "PricerFactory.create(FD1D-GPU).price(host options) -> host prices, pinned input, "
                            "chain compression on"},
-            "gpu_launches": 2 * a.steps,
+            "gpu_launches": launches_per_step * a.steps,
             "clocks": clocks,
         }
         if world == 1 and not a.no_cpu_baseline:

@@ -73,7 +73,9 @@ typedef struct kw_fd1d_config {
     int32_t precision;   /* KW_FD1D_F64 | KW_FD1D_F32 (FD1D.GPU.PRECISION)                   */
     int32_t layout;      /* KW_FD1D_LAYOUT_* (FD1D.GPU.LAYOUT)                               */
     int32_t compress;    /* 1 (default): one PDE per (t,r,q,z,e,w) chain, as the reference's */
-                         /* compression (src/Pricer/kwFd1d.cpp:28-65); 0: one PDE per option */
+                         /* compression (src/Pricer/kwFd1d.cpp:28-65), grouped ON THE DEVICE  */
+                         /* (hash join in HBM; host-side for the SoA layout); 2: grouped on   */
+                         /* the host; 0: one PDE per option                                   */
     int32_t variant;     /* 0 = auto; otherwise a kernel variant id for tuning   */
     int32_t exact;       /* FD1D.GPU.EXACT: 0 (default) carry terms proven < 2^-56 may be    */
                          /* dropped (DESIGN.md "Truncation"); 1: keep all scan levels;       */
@@ -96,7 +98,7 @@ typedef struct kw_fd1d_info {
     int32_t smem_per_cta;     /* bytes                                                       */
     int32_t grid;             /* CTAs launched for the last batch                            */
     int32_t sm_clock_khz;     /* cudaDevAttrClockRate                                        */
-    int32_t reserved;
+    int32_t launches;         /* kernels launched by the last price call                     */
     double last_kernel_ms;    /* device time of the last batch's march launch(es), CUDA events */
     uint64_t last_n_pde;      /* PDEs solved by the last price call                          */
     uint32_t mode_count[6];   /* layout B: PDEs of the last SYNCHRONISED call per carry mode 0..4 */
@@ -117,8 +119,8 @@ void kw_fd1d_destroy(kw_fd1d_handle* h);
  * Does H2D of the options, the whole time march on the device, D2H of the prices. */
 int kw_fd1d_price(kw_fd1d_handle* h, const kw_option* assets, size_t n, double* prices);
 
-/* Same computation with DEVICE-resident buffers, one PDE per option (no chain compression),
- * enqueued on `stream` (a cudaStream_t, may be 0) without synchronising.  Range errors are
+/* Same computation with DEVICE-resident buffers (chain compression on the device when
+ * cfg.compress == 1, otherwise one PDE per option), enqueued on `stream` (a cudaStream_t, may be 0) without synchronising.  Range errors are
  * reported by the next kw_fd1d_sync(). */
 int kw_fd1d_price_device(kw_fd1d_handle* h, const kw_option* d_assets, size_t n, double* d_prices,
                          void* stream);
@@ -129,6 +131,24 @@ int kw_fd1d_sync(kw_fd1d_handle* h, void* stream);
  * "FD1D-BS": FD(as given) + (BS_european - FD_european), Black-Scholes closed form as
  * src/Pricer/kwBlackScholes.cpp:27-50.  HOST buffers. */
 int kw_fd1d_price_bs(kw_fd1d_handle* h, const kw_option* assets, size_t n, double* prices);
+
+/* Device facts for the driver's "Devices Info" block (the historic `kwinto bench -v` output,
+ * reference log/z800_1024_32768.log:21-36). */
+typedef struct kw_fd1d_device_props {
+    char name[128];
+    int32_t integrated;
+    int32_t sm_count;
+    int32_t clock_khz;
+    int32_t regs_per_sm;
+    int32_t max_blocks_per_sm;
+    int32_t max_threads_per_sm;
+    int32_t mem_clock_khz;
+    int32_t mem_bus_width_bits;
+    int32_t reserved;
+    uint64_t total_mem_bytes;
+} kw_fd1d_device_props;
+int kw_fd1d_device_count(void);
+int kw_fd1d_get_device_props(int32_t device, kw_fd1d_device_props* props);
 
 const char* kw_fd1d_last_error(const kw_fd1d_handle* h);
 int kw_fd1d_get_info(const kw_fd1d_handle* h, kw_fd1d_info* info);

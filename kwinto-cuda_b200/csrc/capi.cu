@@ -17,6 +17,7 @@
 #include "fd1d_common.cuh"
 #include "fd1d_reg.cuh"
 #include "fd1d_soa.cuh"
+#include "compress.cuh"
 #include "microbench.cuh"
 
 using namespace kwfd1d;
@@ -114,6 +115,9 @@ __global__ void status_reset_kernel(unsigned int* status)
     status[1] = 0xffffffffu;
     status[2] = status[3] = status[4] = status[5] = status[6] = status[7] = 0u;
 }
+
+// device-side chain compression of `n` device-resident options; fills the batch's PDE tables
+int compress_on_device(kw_fd1d_handle* h, Fd1dBatch& B, const kw_option* d_opts, size_t n, cudaStream_t st);
 
 // BlackScholes_Pricer::priceOne (src/Pricer/kwBlackScholes.cpp:27-50) on European copies and
 // the control-variate combination of src/Pricer/kwFd1d_BlackScholes.cpp:38-40:
@@ -221,6 +225,7 @@ struct kw_fd1d_handle {
     int ctas_per_sm = 0;
     int regs = 0;
     int last_grid = 0;
+    int launches = 0;  // kernels launched by the current / last price call
     uint64_t last_n_pde = 0;
     unsigned int mode_count[6] = {0, 0, 0, 0, 0, 0};
 
@@ -231,6 +236,8 @@ struct kw_fd1d_handle {
     DevBuf<kw_option> d_opts, d_opts2;
     DevBuf<double> d_prices, d_prices2;
     DevBuf<uint32_t> d_rep, d_start, d_csr;
+    DevBuf<uint32_t> d_chain;  // device-side compression: one slab carved into the ChainTable arrays
+    bool dev_compressed = false;
     DevBuf<unsigned int> d_status;
     DevBuf<double> d_soa;
     PinBuf<uint32_t> h_idx;  // rep | start | csr staging
@@ -264,14 +271,16 @@ size_t soa_chunk(const kw_fd1d_handle* h, size_t n_pde)
 int launch_batch(kw_fd1d_handle* h, Fd1dBatch B, cudaStream_t st)
 {
     status_reset_kernel<<<1, 1, 0, st>>>(B.status);
+    h->launches += 1;
     h->last_n_pde = B.n_pde;
     if (h->layout == KW_FD1D_LAYOUT_REG) {
         const RegVariant* v = h->var;
         int grid = h->sm_count * h->ctas_per_sm;
-        if ((uint32_t)grid > B.n_pde) grid = (int)B.n_pde;
+        if ((uint32_t)grid > B.n_pde) grid = (int)B.n_pde;  // with device-side compression n_pde = n is an upper bound
         h->last_grid = grid;
         KW_CUDA(h, cudaEventRecord(h->ev0, st));
         v->fn<<<grid, v->P, v->smem, st>>>(B);
+        h->launches += 1;
         KW_CUDA(h, cudaEventRecord(h->ev1, st));
         h->ev_valid = true;
         KW_CUDA(h, cudaGetLastError());
@@ -302,6 +311,7 @@ int launch_batch(kw_fd1d_handle* h, Fd1dBatch B, cudaStream_t st)
         fd1d_soa_setup_kernel<<<grid, tpb, 0, st>>>(Bc, W);
         fd1d_soa_march_kernel<<<grid, tpb, 0, st>>>(Bc, W);
         fd1d_soa_value_kernel<<<grid, tpb, 0, st>>>(Bc, W);
+        h->launches += 3;
     }
     KW_CUDA(h, cudaEventRecord(h->ev1, st));
     h->ev_valid = true;
@@ -353,6 +363,43 @@ int compress(kw_fd1d_handle* h, const kw_option* a, size_t n, size_t& m, uint32_
     return KW_FD1D_OK;
 }
 
+int compress_on_device(kw_fd1d_handle* h, Fd1dBatch& B, const kw_option* d_opts, size_t n, cudaStream_t st)
+{
+    uint32_t cap = 64;
+    while (cap < 2 * n) cap <<= 1;
+    // slab: slot_rep, slot_cnt, slot_pde [cap] | opt_slot, rep, seg_start, seg_cnt, seg_fill, members [n] | counters [2]
+    KW_CUDA(h, h->d_chain.reserve(3 * (size_t)cap + 6 * n + 2));
+    ChainTable T;
+    uint32_t* p = h->d_chain.p;
+    T.slot_rep = p;
+    T.slot_cnt = p + cap;
+    T.slot_pde = p + 2 * (size_t)cap;
+    p += 3 * (size_t)cap;
+    T.opt_slot = p;
+    T.rep = p + n;
+    T.seg_start = p + 2 * n;
+    T.seg_cnt = p + 3 * n;
+    T.seg_fill = p + 4 * n;
+    T.members = p + 5 * n;
+    T.counters = p + 6 * n;
+    T.cap = cap;
+    const unsigned tpb = 256;
+    chain_reset_kernel<<<(cap + tpb - 1) / tpb, tpb, 0, st>>>(T);
+    chain_insert_kernel<<<(unsigned)((n + tpb - 1) / tpb), tpb, 0, st>>>(d_opts, (uint32_t)n, T);
+    chain_compact_kernel<<<(cap + tpb - 1) / tpb, tpb, 0, st>>>(T);
+    chain_fill_kernel<<<(unsigned)((n + tpb - 1) / tpb), tpb, 0, st>>>((uint32_t)n, T);
+    h->launches += 4;
+    KW_CUDA(h, cudaGetLastError());
+    B.pde_rep = T.rep;
+    B.csr_start = T.seg_start;
+    B.csr_cnt = T.seg_cnt;
+    B.csr_opt = T.members;
+    B.n_pde_dev = T.counters;
+    B.n_pde = (uint32_t)n;  // upper bound (sizes the grid); the kernels read the true count
+    h->dev_compressed = true;
+    return KW_FD1D_OK;
+}
+
 // host assets -> device prices in `d_out` (n doubles) on the handle's stream; no final sync
 int price_to_device(kw_fd1d_handle* h, const kw_option* assets, size_t n, DevBuf<kw_option>& d_opts,
                     double* d_out)
@@ -370,7 +417,10 @@ int price_to_device(kw_fd1d_handle* h, const kw_option* assets, size_t n, DevBuf
     B.density = h->cfg.density;
     B.scale = h->cfg.scale;
     B.max_mode = h->cfg.exact == 0 ? 4 : (h->cfg.exact == 1 ? 1 : 0);
-    if (h->cfg.compress) {
+    h->dev_compressed = false;
+    if (h->cfg.compress == 1 && h->layout == KW_FD1D_LAYOUT_REG) {
+        if (int rc = compress_on_device(h, B, d_opts.p, n, h->stream)) return rc;
+    } else if (h->cfg.compress) {
         size_t m;
         uint32_t *rep, *start, *csr;
         if (int rc = compress(h, assets, n, m, rep, start, csr)) return rc;
@@ -398,6 +448,12 @@ int check_status(kw_fd1d_handle* h, cudaStream_t st, const kw_option* host_asset
     KW_CUDA(h, cudaMemcpyAsync(h->h_status.p, h->d_status.p, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     KW_CUDA(h, cudaStreamSynchronize(st));
     for (int i = 0; i < 6; ++i) h->mode_count[i] = h->h_status.p[2 + i];
+    if (h->dev_compressed) {
+        // the PDE count stayed on the device; it is the sum of the per-mode counters of the march
+        uint64_t m = 0;
+        for (int i = 0; i < 5; ++i) m += h->mode_count[i];
+        h->last_n_pde = m;
+    }
     if (h->h_status.p[0] != 0) {
         const unsigned int idx = h->h_status.p[1];
         if (host_assets) return fail(h, KW_FD1D_ERANGE, range_message(h, host_assets[idx]));
@@ -521,6 +577,7 @@ void kw_fd1d_destroy(kw_fd1d_handle* h)
     h->d_rep.release();
     h->d_start.release();
     h->d_csr.release();
+    h->d_chain.release();
     h->d_status.release();
     h->d_soa.release();
     h->h_idx.release();
@@ -533,6 +590,7 @@ void kw_fd1d_destroy(kw_fd1d_handle* h)
 
 int kw_fd1d_price(kw_fd1d_handle* h, const kw_option* assets, size_t n, double* prices)
 {
+    if (h) h->launches = 0;
     if (!h) return KW_FD1D_EINVAL;
     if (!h->stream) return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::price: pricer was not initialised");
     h->err.clear();
@@ -548,6 +606,7 @@ int kw_fd1d_price(kw_fd1d_handle* h, const kw_option* assets, size_t n, double* 
 
 int kw_fd1d_price_bs(kw_fd1d_handle* h, const kw_option* assets, size_t n, double* prices)
 {
+    if (h) h->launches = 0;
     if (!h) return KW_FD1D_EINVAL;
     if (!h->stream) return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::price: pricer was not initialised");
     h->err.clear();
@@ -565,6 +624,7 @@ int kw_fd1d_price_bs(kw_fd1d_handle* h, const kw_option* assets, size_t n, doubl
     if (int rc = price_to_device(h, euro.data(), n, h->d_opts2, h->d_prices2.p)) return rc;
     // 3. + (BS - FD_euro) (:30-40)
     bs_combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_opts2.p, n, h->d_prices.p, h->d_prices2.p);
+    h->launches += 1;
     KW_CUDA(h, cudaGetLastError());
     KW_CUDA(h, cudaMemcpyAsync(prices, h->d_prices.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     return check_status(h, h->stream, euro.data());
@@ -572,6 +632,7 @@ int kw_fd1d_price_bs(kw_fd1d_handle* h, const kw_option* assets, size_t n, doubl
 
 int kw_fd1d_price_device(kw_fd1d_handle* h, const kw_option* d_assets, size_t n, double* d_prices, void* stream)
 {
+    if (h) h->launches = 0;
     if (!h) return KW_FD1D_EINVAL;
     if (!h->stream) return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::price: pricer was not initialised");
     h->err.clear();
@@ -589,6 +650,9 @@ int kw_fd1d_price_device(kw_fd1d_handle* h, const kw_option* d_assets, size_t n,
     B.density = h->cfg.density;
     B.scale = h->cfg.scale;
     B.max_mode = h->cfg.exact == 0 ? 4 : (h->cfg.exact == 1 ? 1 : 0);
+    h->dev_compressed = false;
+    if (h->cfg.compress == 1 && h->layout == KW_FD1D_LAYOUT_REG)
+        if (int rc = compress_on_device(h, B, d_assets, n, (cudaStream_t)stream)) return rc;
     return launch_batch(h, B, (cudaStream_t)stream);
 }
 
@@ -598,6 +662,31 @@ int kw_fd1d_sync(kw_fd1d_handle* h, void* stream)
     if (!h->stream) return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer: pricer was not initialised");
     KW_CUDA(h, cudaSetDevice(h->cfg.device));
     return check_status(h, (cudaStream_t)stream, nullptr);
+}
+
+int kw_fd1d_device_count(void)
+{
+    int n = 0;
+    return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
+
+int kw_fd1d_get_device_props(int32_t device, kw_fd1d_device_props* out)
+{
+    if (!out) return KW_FD1D_EINVAL;
+    memset(out, 0, sizeof *out);
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, device) != cudaSuccess) return KW_FD1D_ECUDA;
+    strncpy(out->name, p.name, sizeof out->name - 1);
+    out->integrated = p.integrated;
+    out->sm_count = p.multiProcessorCount;
+    out->regs_per_sm = p.regsPerMultiprocessor;
+    out->max_blocks_per_sm = p.maxBlocksPerMultiProcessor;
+    out->max_threads_per_sm = p.maxThreadsPerMultiProcessor;
+    out->mem_bus_width_bits = p.memoryBusWidth;
+    out->total_mem_bytes = p.totalGlobalMem;
+    cudaDeviceGetAttribute(&out->clock_khz, cudaDevAttrClockRate, device);
+    cudaDeviceGetAttribute(&out->mem_clock_khz, cudaDevAttrMemoryClockRate, device);
+    return KW_FD1D_OK;
 }
 
 const char* kw_fd1d_last_error(const kw_fd1d_handle* h) { return h ? h->err.c_str() : "null handle"; }
@@ -618,6 +707,7 @@ int kw_fd1d_get_info(const kw_fd1d_handle* hc, kw_fd1d_info* info)
     info->smem_per_cta = h->var ? (int)h->var->smem : 0;
     info->grid = h->last_grid;
     info->sm_clock_khz = h->clock_khz;
+    info->launches = h->launches;
     info->last_n_pde = h->last_n_pde;
     for (int i = 0; i < 6; ++i) info->mode_count[i] = h->mode_count[i];
     info->last_kernel_ms = 0.;

@@ -29,6 +29,9 @@ struct Fd1dBatch {
     const uint32_t* pde_rep;
     const uint32_t* csr_start;
     const uint32_t* csr_opt;
+    const uint32_t* csr_cnt;    // device-side compression (compress.cuh): members per PDE; then
+                                // csr_start[p] is the segment start and there is no csr_start[m]
+    const uint32_t* n_pde_dev;  // device-side compression: the PDE count lives in HBM (overrides n_pde)
     double* prices;
     unsigned int* status;  // [0] = number of out-of-range options, [1] = smallest such index,
                            // [2..6] = PDEs marched in carry mode 0..4 (layout B)
@@ -40,6 +43,26 @@ struct Fd1dBatch {
     double density;
     double scale;
 };
+
+__device__ __forceinline__ uint32_t batch_n_pde(const Fd1dBatch& B)
+{
+    return B.n_pde_dev ? __ldg(B.n_pde_dev) : B.n_pde;
+}
+
+// [q0, q1) = this PDE's entries of csr_opt
+__device__ __forceinline__ void chain_range(const Fd1dBatch& B, uint32_t pde, uint32_t& q0, uint32_t& q1)
+{
+    if (!B.csr_start) {
+        q0 = pde;
+        q1 = pde + 1;
+    } else if (B.csr_cnt) {
+        q0 = __ldg(B.csr_start + pde);
+        q1 = q0 + __ldg(B.csr_cnt + pde);
+    } else {
+        q0 = __ldg(B.csr_start + pde);
+        q1 = __ldg(B.csr_start + pde + 1);
+    }
+}
 
 struct PdeScalars {
     double a0, ax, axx;  // src/Pricer/kwFd1d.cpp:80-83

@@ -231,7 +231,8 @@ __global__ void __launch_bounds__(P, MINB) fd1d_reg_kernel(const Fd1dBatch B)
         tbase = s_taddr + ((uint32_t)(warp & 3) << 21);  // lane field (bits 31:16) = 32 * (warp % 4)
     }
 
-    for (uint32_t pde = blockIdx.x; pde < B.n_pde; pde += gridDim.x) {
+    const uint32_t n_pde = batch_n_pde(B);
+    for (uint32_t pde = blockIdx.x; pde < n_pde; pde += gridDim.x) {
         const uint32_t rep = B.pde_rep ? __ldg(B.pde_rep + pde) : pde;
         const kw_option opt = load_option(B.opts + rep);
         const PdeScalars sc = pde_scalars(opt, B);
@@ -827,8 +828,8 @@ __global__ void __launch_bounds__(P, MINB) fd1d_reg_kernel(const Fd1dBatch B)
         for (int i = 0; i < M; ++i) scr[k * M + i] = (double)vm[i];
         __syncthreads();
         {
-            const uint32_t q0 = B.csr_start ? __ldg(B.csr_start + pde) : pde;
-            const uint32_t q1 = B.csr_start ? __ldg(B.csr_start + pde + 1) : pde + 1;
+            uint32_t q0, q1;
+            chain_range(B, pde, q0, q1);
             for (uint32_t q = q0 + k; q < q1; q += P) {
                 const uint32_t oi = B.csr_opt ? __ldg(B.csr_opt + q) : q;
                 price_option(B, oi, [&](int j) { return xs[j]; }, [&](int j) { return scr[j]; });

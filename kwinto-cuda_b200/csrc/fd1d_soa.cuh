@@ -104,8 +104,8 @@ __global__ void __launch_bounds__(128) fd1d_soa_value_kernel(const Fd1dBatch B, 
     const size_t n = W.n;
     const double* X = W.X + i;
     const double* V = W.V + i;
-    const uint32_t q0 = B.csr_start ? __ldg(B.csr_start + pde) : pde;
-    const uint32_t q1 = B.csr_start ? __ldg(B.csr_start + pde + 1) : pde + 1;
+    uint32_t q0, q1;
+    chain_range(B, pde, q0, q1);
     for (uint32_t q = q0; q < q1; ++q) {
         const uint32_t oi = B.csr_opt ? __ldg(B.csr_opt + q) : q;
         price_option(B, oi, [&](int j) { return X[(size_t)j * n]; }, [&](int j) { return V[(size_t)j * n]; });

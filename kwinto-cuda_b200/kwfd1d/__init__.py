@@ -42,7 +42,7 @@ class _CInfo(C.Structure):  # struct kw_fd1d_info
     _fields_ = [("device", C.c_int32), ("sm_count", C.c_int32), ("layout", C.c_int32), ("variant", C.c_int32),
                 ("threads_per_pde", C.c_int32), ("nodes_per_thread", C.c_int32), ("ctas_per_sm", C.c_int32),
                 ("regs_per_thread", C.c_int32), ("smem_per_cta", C.c_int32), ("grid", C.c_int32),
-                ("sm_clock_khz", C.c_int32), ("reserved", C.c_int32), ("last_kernel_ms", C.c_double),
+                ("sm_clock_khz", C.c_int32), ("launches", C.c_int32), ("last_kernel_ms", C.c_double),
                 ("last_n_pde", C.c_uint64), ("mode_count", C.c_uint32 * 6), ("device_name", C.c_char * 128)]
 
 
@@ -92,7 +92,7 @@ def load_library(path: str = LIB_PATH):
 
 EXPORTED_SYMBOLS = [  # every entry point include/kw_fd1d.h declares
     "kw_fd1d_config_default", "kw_fd1d_create", "kw_fd1d_destroy", "kw_fd1d_price", "kw_fd1d_price_device",
-    "kw_fd1d_sync", "kw_fd1d_price_bs", "kw_fd1d_last_error", "kw_fd1d_get_info", "kw_fd1d_fp64_peak",
+    "kw_fd1d_sync", "kw_fd1d_price_bs", "kw_fd1d_device_count", "kw_fd1d_get_device_props", "kw_fd1d_last_error", "kw_fd1d_get_info", "kw_fd1d_fp64_peak",
     "kw_fd1d_microbench", "kw_fd1d_tmem_probe", "kw_fd1d_dfma_probe", "kw_fd1d_version",
 ]
 

@@ -114,6 +114,34 @@ def test_other_variants(variant, x, oracle):
     assert err == "" and maxdiff(got, want) <= TOL, (variant, maxdiff(got, want))
 
 
+def test_device_side_compression_matches_host_side():
+    """FD1D.GPU.COMPRESS = 1 groups the chains with a hash join in HBM (compress.cuh), 2 on the host (the
+    reference's sort, src/Pricer/kwFd1d.cpp:28-65, replaced by a hash map), 0 not at all: same prices,
+    bit for bit, and the same number of PDEs as the reference finds (600 chains in the fixture)."""
+    g = load_golden("portfolio_fd1d")
+    o = g["options"]
+    res = {}
+    for c in (0, 1, 2):
+        p = make_pricer(128, 512, **{"FD1D.GPU.COMPRESS": c})
+        err, got = p.price(o)
+        assert err == ""
+        res[c] = got
+        assert p.info()["last_n_pde"] == (6000 if c == 0 else 600), (c, p.info()["last_n_pde"])
+    assert np.array_equal(res[0], res[1]) and np.array_equal(res[1], res[2])
+    # many members per chain, more chains than resident CTAs, a NaN key and a -0.0 key in the batch
+    rng = np.random.default_rng(5)
+    base = g["options"][::10][:600].copy()
+    big = base[rng.integers(0, 600, size=50000)]
+    big["k"] = rng.uniform(60., 140., size=big.shape[0])
+    big["s"] = 100.
+    a = make_pricer(64, 256, **{"FD1D.GPU.COMPRESS": 1})
+    b = make_pricer(64, 256, **{"FD1D.GPU.COMPRESS": 0})
+    err, pa = a.price(big)
+    assert err == "" and a.info()["last_n_pde"] == len(np.unique(big[["t", "r", "q", "z", "e", "w"]]))
+    err, pb = b.price(big)
+    assert err == "" and np.array_equal(pa, pb)
+
+
 @pytest.mark.parametrize("variant", [221, 222])
 def test_tmem_variants_all_modes_and_reuse(variant, oracle):
     """Tensor-memory variants: every carry mode (forced through FD1D.GPU.EXACT), more PDEs than resident
