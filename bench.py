@@ -314,7 +314,8 @@ def main():
         roofline = {
             "bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "traffic": traffic,
-            "kernel": f"fd1d_{info['layout']}_kernel variant {info['variant']}", "kernel_ms": k_ms,
+            "kernel": (f"fd1d_warp_kernel (Layout W) variant {info['variant']}" if info["threads_per_pde"] == 32 and a.x > 256
+                       else f"fd1d_{info['layout']}_kernel variant {info['variant']}"), "kernel_ms": k_ms,
             "algorithmic_flop_per_option": F, "options_per_launch": n,
             "peak_source": ("measured here: DFMA throughput probe kw_fd1d_fp64_peak (MEASURED_PEAKS.json has no "
                             "FP64 figure)" if peak_meas else "nominal"),

@@ -17,6 +17,7 @@
 #include "fd1d_common.cuh"
 #include "fd1d_reg.cuh"
 #include "fd1d_soa.cuh"
+#include "fd1d_warp.cuh"
 #include "compress.cuh"
 #include "microbench.cuh"
 
@@ -34,6 +35,7 @@ struct RegVariant {
     RegKernel fn;
     size_t smem;
     int tmem_cols;  // tensor-memory columns each CTA allocates (0 = none)
+    int pdes_per_cta;  // 0/1: one PDE per CTA (Layout B); 4: one PDE per warp (Layout W)
 };
 
 #define KW_VARIANT(ID, M_, P_, MINB_, PJ_, DQ_)                                                   \
@@ -52,6 +54,11 @@ struct RegVariant {
         ID, KW_FD1D_F64, 8, 128, MINB_, false, false, fd1d_reg_kernel<double, 8, 128, MINB_, false, false, ICMP_, true>, \
             RegSmem<8, 128>::bytes(false, false), 128                                              \
     }
+#define KW_VARIANT_W(ID, MINB_, ICMP_)                                                            \
+    {                                                                                              \
+        ID, KW_FD1D_F64, 8, 128, MINB_, false, false, fd1d_warp_kernel<4, MINB_, ICMP_>,           \
+            WarpSmem<4>::bytes(), 256, 4                                                           \
+    }
 #define KW_VARIANT_F32(ID, M_, P_, MINB_)                                                         \
     {                                                                                              \
         ID, KW_FD1D_F32, M_, P_, MINB_, false, false, fd1d_reg_kernel<float, M_, P_, MINB_, false, false>, \
@@ -65,7 +72,8 @@ const RegVariant g_variants[] = {
     KW_VARIANT(101, 8, 64, 6, false, false),   // x <= 512
     KW_VARIANT(102, 8, 64, 8, true, true),
     KW_VARIANT(103, 8, 64, 6, true, false),
-    KW_VARIANT(201, 8, 128, 3, false, false),  // x <= 1024
+    KW_VARIANT_W(231, 2, false),               // x <= 1024: Layout W (warp per PDE, coefficients in tensor memory)
+    KW_VARIANT(201, 8, 128, 3, false, false),  // x <= 1024, CTA per PDE (batches below one wave of Layout W)
     KW_VARIANT(202, 8, 128, 3, true, false),
     KW_VARIANT(203, 8, 128, 4, true, true),
     KW_VARIANT(204, 8, 128, 4, true, false),
@@ -74,6 +82,7 @@ const RegVariant g_variants[] = {
     KW_VARIANT_I(213, 8, 128, 4, true, true),
     KW_VARIANT_T(221, 4, false),  // coefficient arrays in tensor memory, 4 PDEs per SM
     KW_VARIANT_T(222, 4, true),
+    KW_VARIANT_W(232, 2, true),
     KW_VARIANT(301, 8, 256, 1, false, false),  // x <= 2048
     KW_VARIANT(302, 8, 256, 2, true, true),
     KW_VARIANT(401, 8, 512, 1, true, true),    // x <= 4096
@@ -221,9 +230,14 @@ struct kw_fd1d_handle {
     char name[128] = {0};
 
     int layout = 0;
-    const RegVariant* var = nullptr;
+    const RegVariant* var = nullptr;        // variant for batches that fill the device
     int ctas_per_sm = 0;
     int regs = 0;
+    const RegVariant* var_small = nullptr;  // auto dispatch only: variant for batches below `small_below` PDEs
+    int ctas_per_sm_small = 0;
+    int regs_small = 0;
+    uint32_t small_below = 0;
+    const RegVariant* last_var = nullptr;   // what the last batch ran
     int last_grid = 0;
     int launches = 0;  // kernels launched by the current / last price call
     uint64_t last_n_pde = 0;
@@ -261,6 +275,9 @@ int fail(kw_fd1d_handle* h, int code, const std::string& msg)
                             " at " #call);                                                     \
     } while (0)
 
+int prepare_variant(kw_fd1d_handle* h, const RegVariant* var, const cudaDeviceProp& prop, int& ctas_per_sm, int& regs);
+const RegVariant* find_small_variant(int xDim, int prec);
+
 size_t soa_chunk(const kw_fd1d_handle* h, size_t n_pde)
 {
     (void)h;
@@ -274,9 +291,13 @@ int launch_batch(kw_fd1d_handle* h, Fd1dBatch B, cudaStream_t st)
     h->launches += 1;
     h->last_n_pde = B.n_pde;
     if (h->layout == KW_FD1D_LAYOUT_REG) {
-        const RegVariant* v = h->var;
-        int grid = h->sm_count * h->ctas_per_sm;
-        if ((uint32_t)grid > B.n_pde) grid = (int)B.n_pde;  // with device-side compression n_pde = n is an upper bound
+        const bool small = h->var_small && B.n_pde < h->small_below;
+        const RegVariant* v = small ? h->var_small : h->var;
+        h->last_var = v;
+        int grid = h->sm_count * (small ? h->ctas_per_sm_small : h->ctas_per_sm);
+        const uint32_t ppc = v->pdes_per_cta > 1 ? (uint32_t)v->pdes_per_cta : 1u;
+        const uint32_t want = (B.n_pde + ppc - 1) / ppc;  // with device-side compression n_pde = n is an upper bound
+        if ((uint32_t)grid > want) grid = (int)want;
         h->last_grid = grid;
         KW_CUDA(h, cudaEventRecord(h->ev0, st));
         v->fn<<<grid, v->P, v->smem, st>>>(B);
@@ -451,7 +472,7 @@ int check_status(kw_fd1d_handle* h, cudaStream_t st, const kw_option* host_asset
     if (h->dev_compressed) {
         // the PDE count stayed on the device; it is the sum of the per-mode counters of the march
         uint64_t m = 0;
-        for (int i = 0; i < 5; ++i) m += h->mode_count[i];
+        for (int i = 0; i < 6; ++i) m += h->mode_count[i];
         h->last_n_pde = m;
     }
     if (h->h_status.p[0] != 0) {
@@ -461,6 +482,47 @@ int check_status(kw_fd1d_handle* h, cudaStream_t st, const kw_option* host_asset
                     "Fd1d_Pricer::price Fd1d::value: x not in range (option " + std::to_string(idx) + ")");
     }
     return KW_FD1D_OK;
+}
+
+
+// occupancy and attributes of one kernel variant
+int prepare_variant(kw_fd1d_handle* h, const RegVariant* var, const cudaDeviceProp& prop, int& ctas_per_sm, int& regs)
+{
+    KW_CUDA(h, cudaFuncSetAttribute(var->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)var->smem));
+    cudaFuncAttributes fa;
+    KW_CUDA(h, cudaFuncGetAttributes(&fa, var->fn));
+    regs = fa.numRegs;
+    int occ = 0;
+    KW_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, var->fn, var->P, var->smem));
+    if (occ < 1) return fail(h, KW_FD1D_ECUDA, "Fd1dGpu_Pricer::init: kernel variant does not fit on an SM");
+    if (var->tmem_cols > 0) {
+        // The occupancy calculator answers 1 for any kernel that allocates tensor memory, but the
+        // hardware co-schedules CTAs as long as their tcgen05.alloc requests fit the SM's 512 columns
+        // (measured: kw_fd1d_tmem_probe finds 4 x 128 columns resident).  Size the persistent grid
+        // from the real limits: registers, shared memory, TMEM columns.
+        const int by_regs = 65536 / (fa.numRegs * var->P);
+        const int by_smem = (int)((size_t)prop.sharedMemPerMultiprocessor / (var->smem + 1024));
+        const int by_tmem = 512 / var->tmem_cols;
+        occ = std::max(1, std::min({by_regs, by_smem, by_tmem, var->minb}));
+        // ... and ask for the shared-memory carve-out that many CTAs need (the driver would size it
+        // for the single CTA the calculator believes in)
+        KW_CUDA(h, cudaFuncSetAttribute(var->fn, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                        cudaSharedmemCarveoutMaxShared));
+    }
+    ctas_per_sm = occ;
+    return KW_FD1D_OK;
+}
+
+// the first CTA-per-PDE entry of the smallest fitting tile
+const RegVariant* find_small_variant(int xDim, int prec)
+{
+    const RegVariant* best = nullptr;
+    for (int i = 0; i < kNumVariants; ++i) {
+        const RegVariant& v = g_variants[i];
+        if (v.M * v.P < xDim || v.prec != prec || v.pdes_per_cta > 1 || v.tmem_cols > 0) continue;
+        if (!best || v.P < best->P) best = &v;
+    }
+    return best;
 }
 
 }  // namespace
@@ -522,28 +584,16 @@ int kw_fd1d_create(const kw_fd1d_config* cfg, kw_fd1d_handle** out)
         h->var = find_variant((int)cfg->x_grid_size, cfg->variant, cfg->precision);
         if (!h->var)
             return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::init: no register-layout kernel variant for this FD1D.X_GRID_SIZE / FD1D.GPU.VARIANT");
-        KW_CUDA(h, cudaFuncSetAttribute(h->var->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->var->smem));
-        cudaFuncAttributes fa;
-        KW_CUDA(h, cudaFuncGetAttributes(&fa, h->var->fn));
-        h->regs = fa.numRegs;
-        int occ = 0;
-        KW_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, h->var->fn, h->var->P, h->var->smem));
-        if (occ < 1) return fail(h, KW_FD1D_ECUDA, "Fd1dGpu_Pricer::init: kernel variant does not fit on an SM");
-        if (h->var->tmem_cols > 0) {
-            // The occupancy calculator answers 1 for any kernel that allocates tensor memory, but the
-            // hardware co-schedules CTAs as long as their tcgen05.alloc requests fit the SM's 512 columns
-            // (measured: kw_fd1d_tmem_probe finds 4 x 128 columns resident).  Size the persistent grid
-            // from the real limits: registers, shared memory, TMEM columns.
-            const int by_regs = 65536 / (fa.numRegs * h->var->P);
-            const int by_smem = (int)((size_t)prop.sharedMemPerMultiprocessor / (h->var->smem + 1024));
-            const int by_tmem = 512 / h->var->tmem_cols;
-            occ = std::max(1, std::min({by_regs, by_smem, by_tmem, h->var->minb}));
-            // ... and ask for the shared-memory carve-out that many CTAs need (the driver would size it
-            // for the single CTA the calculator believes in)
-            KW_CUDA(h, cudaFuncSetAttribute(h->var->fn, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                            cudaSharedmemCarveoutMaxShared));
+        if (int rc = prepare_variant(h, h->var, prop, h->ctas_per_sm, h->regs)) return rc;
+        if (cfg->variant == 0 && h->var->pdes_per_cta > 1) {
+            // Layout W packs 4 PDEs into a CTA and 8 into an SM: below one full wave of the device the
+            // CTA-per-PDE kernel spreads the batch over more SMs (DESIGN.md "dispatch")
+            h->var_small = find_small_variant((int)cfg->x_grid_size, cfg->precision);
+            if (h->var_small) {
+                if (int rc = prepare_variant(h, h->var_small, prop, h->ctas_per_sm_small, h->regs_small)) return rc;
+                h->small_below = (uint32_t)(h->sm_count * h->ctas_per_sm * h->var->pdes_per_cta);
+            }
         }
-        h->ctas_per_sm = occ;
     } else if (layout == KW_FD1D_LAYOUT_SOA) {
         if (cfg->precision != KW_FD1D_F64)
             return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::init: the SoA layout (FD1D.GPU.LAYOUT = soa) is fp64 only");
@@ -699,12 +749,14 @@ int kw_fd1d_get_info(const kw_fd1d_handle* hc, kw_fd1d_info* info)
     info->device = h->cfg.device;
     info->sm_count = h->sm_count;
     info->layout = h->layout;
-    info->variant = h->var ? h->var->id : 0;
-    info->threads_per_pde = h->var ? h->var->P : 1;
-    info->nodes_per_thread = h->var ? h->var->M : (int)h->cfg.x_grid_size;
-    info->ctas_per_sm = h->ctas_per_sm;
-    info->regs_per_thread = h->regs;
-    info->smem_per_cta = h->var ? (int)h->var->smem : 0;
+    const RegVariant* lv = h->last_var ? h->last_var : h->var;
+    const bool lsmall = lv && lv == h->var_small;
+    info->variant = lv ? lv->id : 0;
+    info->threads_per_pde = lv ? (lv->pdes_per_cta > 1 ? 32 : lv->P) : 1;
+    info->nodes_per_thread = lv ? (lv->pdes_per_cta > 1 ? lv->M * lv->pdes_per_cta : lv->M) : (int)h->cfg.x_grid_size;
+    info->ctas_per_sm = lsmall ? h->ctas_per_sm_small : h->ctas_per_sm;
+    info->regs_per_thread = lsmall ? h->regs_small : h->regs;
+    info->smem_per_cta = lv ? (int)lv->smem : 0;
     info->grid = h->last_grid;
     info->sm_clock_khz = h->clock_khz;
     info->launches = h->launches;

@@ -167,6 +167,138 @@ __device__ __forceinline__ float max_like_icmp(float a, float b)
     return (__float_as_int(a) < __float_as_int(b)) ? b : a;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Set-up shared by the CTA-per-PDE kernel below and the warp-per-PDE kernel (fd1d_warp.cuh): P
+// threads, thread k owns the M nodes of chunk k.  Fills the x grid (xs, shared), the payoff v, the
+// projection floor pj (no_floor where the reference does not project) and the pivot-scaled LU of
+// B = 1 - dt/2 A:  a~ (a[0] = chunk-entry multiplier), g~ (g[M-1] = chunk-exit), D = 2/beta.
+// `scr` is >= 8*P doubles of shared scratch.  Contains __syncthreads(): call from every thread.
+template <int M, int P>
+__device__ __forceinline__ void setup_lu(const Fd1dBatch& B, const PdeScalars& sc, double no_floor, double* xs,
+                                         double* scr, double (&v)[M], double (&pj)[M], double (&a)[M],
+                                         double (&g)[M], double (&D)[M])
+{
+    constexpr int N = M * P;
+    const int k = threadIdx.x;
+    const int lane = k & 31;
+    const int warp = k >> 5;
+    const int xDim = B.xDim;
+    double* s_bu_last = scr;           // [P]
+    double* s_mat = scr + P;           // [4][P]
+    double* s_bin = scr + 5 * P;       // [P] pivot just before each chunk
+    double* s_ib_first = scr + 6 * P;  // [P]
+    double* s_ib_last = scr + 7 * P;   // [P]
+    // ---------------- set-up: grid, payoff --------------------------------------------
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+        const int j = k * M + i;
+        const double x = x_node(sc, B.density, j);
+        xs[j] = x;
+        double p = 0.;
+        if (j < xDim) p = payoff_node(sc.put, x);
+        v[i] = p;
+        // projection skips the last node (src/Math/kwFd1d.cpp:130); European: never
+        pj[i] = (sc.american && j < xDim - 1) ? p : no_floor;
+    }
+    __syncthreads();
+
+    // ---------------- B rows, Moebius-composed pivots ---------------------------------
+    {
+        double bl[M], bb[M], bu[M];
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+            const int j = k * M + i;
+            const double xm = xs[j > 0 ? j - 1 : 0];
+            const double xp = xs[j < N - 1 ? j + 1 : N - 1];
+            b_row(sc, j, xDim, xm, xs[j], xp, bl[i], bb[i], bu[i]);
+        }
+        s_bu_last[k] = bu[M - 1];
+        __syncthreads();
+        const double bu_prev = k > 0 ? s_bu_last[k - 1] : 0.;
+
+        // beta_j = b_j - c_j / beta_{j-1}, c_j = bl_j * bu_{j-1}: as a Moebius map on
+        // (num; den) it is [[b_j, -c_j], [1, 0]]; compose the chunk's M maps
+        {
+            Mat2 m = {1., 0., 0., 1.};
+#pragma unroll
+            for (int i = 0; i < M; ++i) {
+                const double c = bl[i] * (i ? bu[i - 1] : bu_prev);
+                Mat2 n;
+                n.m00 = fma(bb[i], m.m00, -c * m.m10);
+                n.m01 = fma(bb[i], m.m01, -c * m.m11);
+                n.m10 = m.m00;
+                n.m11 = m.m01;
+                m = n;
+                if ((i & 3) == 3) mat_normalise(m);
+            }
+            s_mat[k] = m.m00;
+            s_mat[P + k] = m.m01;
+            s_mat[2 * P + k] = m.m10;
+            s_mat[3 * P + k] = m.m11;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            constexpr int CPL = P / 32;  // chunk maps per lane
+            Mat2 Lm = {1., 0., 0., 1.};
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                const int idx = lane * CPL + c;
+                const Mat2 m = {s_mat[idx], s_mat[P + idx], s_mat[2 * P + idx], s_mat[3 * P + idx]};
+                Lm = mat_mul(m, Lm);
+                mat_normalise(Lm);
+            }
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const Mat2 o = mat_shfl_up(Lm, d);
+                if (lane >= d) {
+                    Lm = mat_mul(Lm, o);
+                    mat_normalise(Lm);
+                }
+            }
+            const Mat2 E = mat_shfl_up(Lm, 1);
+            double num = lane ? E.m00 : 1.;
+            double den = lane ? E.m10 : 0.;
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+                const int idx = lane * CPL + c;
+                s_bin[idx] = den == 0. ? CUDART_INF : num / den;
+                const double nn = fma(s_mat[idx], num, s_mat[P + idx] * den);
+                const double dd = fma(s_mat[2 * P + idx], num, s_mat[3 * P + idx] * den);
+                const double s = 1. / fmax(fabs(nn), fabs(dd));
+                num = nn * s;
+                den = dd * s;
+            }
+        }
+        __syncthreads();
+
+        // pivots inside the chunk, in the reference's order (src/Math/kwMath.cpp:32-33):
+        // gam = au[j-1] / bet;  bet = a[j] - al[j] * gam
+        double ib[M];
+        {
+            double prev = s_bin[k];
+#pragma unroll
+            for (int i = 0; i < M; ++i) {
+                const double gam = (i ? bu[i - 1] : bu_prev) / prev;
+                const double beta = __dsub_rn(bb[i], __dmul_rn(bl[i], gam));
+                ib[i] = 1. / beta;
+                prev = beta;
+            }
+        }
+        s_ib_first[k] = ib[0];
+        s_ib_last[k] = ib[M - 1];
+        __syncthreads();
+        const double ib_prev = k > 0 ? s_ib_last[k - 1] : 0.;
+        const double ib_next = k < P - 1 ? s_ib_first[k + 1] : 0.;
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+            const int j = k * M + i;
+            a[i] = -bl[i] * (i ? ib[i - 1] : ib_prev);
+            g[i] = -bu[i] * (i < M - 1 ? ib[i + 1] : ib_next);
+            D[i] = j < xDim ? 2. * ib[i] : 0.;
+        }
+    }
+}
+
 // PROJ_SMEM / DQ_SMEM: keep the projection floor / the D*Q fix-up array in shared memory
 // instead of registers (fewer registers -> more CTAs per SM, more shared-memory wavefronts).
 // F: the arithmetic type of the time march.  double = the parity path (1e-9 absolute); float =
@@ -207,13 +339,6 @@ __global__ void __launch_bounds__(P, MINB) fd1d_reg_kernel(const Fd1dBatch B)
     double* s_af4 = H0 + NW;             // [P] level-4 forward multipliers (general mode only)
     double* s_gb4 = s_af4 + P;           // [P] level-4 backward multipliers (general mode only)
 
-    // scratch sub-arrays used during set-up
-    double* s_bu_last = scr;           // [P]
-    double* s_mat = scr + P;           // [4][P]
-    double* s_bin = scr + 5 * P;       // [P] pivot just before each chunk
-    double* s_ib_first = scr + 6 * P;  // [P]
-    double* s_ib_last = scr + 7 * P;   // [P]
-
     const int k = threadIdx.x;
     const int lane = k & 31;
     const int warp = k >> 5;
@@ -237,122 +362,15 @@ __global__ void __launch_bounds__(P, MINB) fd1d_reg_kernel(const Fd1dBatch B)
         const kw_option opt = load_option(B.opts + rep);
         const PdeScalars sc = pde_scalars(opt, B);
 
-        // ---------------- set-up: grid, payoff --------------------------------------------
+        // ---------------- set-up: grid, payoff, B rows, Moebius-composed pivots -------------
         double v[M], pj[M];
-#pragma unroll
-        for (int i = 0; i < M; ++i) {
-            const int j = k * M + i;
-            const double x = x_node(sc, B.density, j);
-            xs[j] = x;
-            double p = 0.;
-            if (j < xDim) p = payoff_node(sc.put, x);
-            v[i] = p;
-            // projection skips the last node (src/Math/kwFd1d.cpp:130); European: never
-            pj[i] = (sc.american && j < xDim - 1) ? p : (ICMP ? -0. : -CUDART_INF);
-        }
-        if (PROJ_SMEM) {
-#pragma unroll
-            for (int c = 0; c < M2; ++c) proj2[c * P + k] = make_double2(pj[2 * c], pj[2 * c + 1]);
-        }
-        __syncthreads();
-
-        // ---------------- B rows, Moebius-composed pivots ---------------------------------
         double a[M], g[M], D[M];  // a~ (a[0] = chunk-entry multiplier), g~ (g[M-1] = chunk-exit), 2/beta
         double DR[M], DQ[M];
         double Af[4], Gb[4], PWexf, PWbs, R0n, Hs, G0;
-        {
-            double bl[M], bb[M], bu[M];
+        setup_lu<M, P>(B, sc, ICMP ? -0. : -CUDART_INF, xs, scr, v, pj, a, g, D);
+        if (PROJ_SMEM) {
 #pragma unroll
-            for (int i = 0; i < M; ++i) {
-                const int j = k * M + i;
-                const double xm = xs[j > 0 ? j - 1 : 0];
-                const double xp = xs[j < N - 1 ? j + 1 : N - 1];
-                b_row(sc, j, xDim, xm, xs[j], xp, bl[i], bb[i], bu[i]);
-            }
-            s_bu_last[k] = bu[M - 1];
-            __syncthreads();
-            const double bu_prev = k > 0 ? s_bu_last[k - 1] : 0.;
-
-            // beta_j = b_j - c_j / beta_{j-1}, c_j = bl_j * bu_{j-1}: as a Moebius map on
-            // (num; den) it is [[b_j, -c_j], [1, 0]]; compose the chunk's M maps
-            {
-                Mat2 m = {1., 0., 0., 1.};
-#pragma unroll
-                for (int i = 0; i < M; ++i) {
-                    const double c = bl[i] * (i ? bu[i - 1] : bu_prev);
-                    Mat2 n;
-                    n.m00 = fma(bb[i], m.m00, -c * m.m10);
-                    n.m01 = fma(bb[i], m.m01, -c * m.m11);
-                    n.m10 = m.m00;
-                    n.m11 = m.m01;
-                    m = n;
-                    if ((i & 3) == 3) mat_normalise(m);
-                }
-                s_mat[k] = m.m00;
-                s_mat[P + k] = m.m01;
-                s_mat[2 * P + k] = m.m10;
-                s_mat[3 * P + k] = m.m11;
-            }
-            __syncthreads();
-            if (warp == 0) {
-                constexpr int CPL = P / 32;  // chunk maps per lane
-                Mat2 Lm = {1., 0., 0., 1.};
-#pragma unroll
-                for (int c = 0; c < CPL; ++c) {
-                    const int idx = lane * CPL + c;
-                    const Mat2 m = {s_mat[idx], s_mat[P + idx], s_mat[2 * P + idx], s_mat[3 * P + idx]};
-                    Lm = mat_mul(m, Lm);
-                    mat_normalise(Lm);
-                }
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const Mat2 o = mat_shfl_up(Lm, d);
-                    if (lane >= d) {
-                        Lm = mat_mul(Lm, o);
-                        mat_normalise(Lm);
-                    }
-                }
-                const Mat2 E = mat_shfl_up(Lm, 1);
-                double num = lane ? E.m00 : 1.;
-                double den = lane ? E.m10 : 0.;
-#pragma unroll
-                for (int c = 0; c < CPL; ++c) {
-                    const int idx = lane * CPL + c;
-                    s_bin[idx] = den == 0. ? CUDART_INF : num / den;
-                    const double nn = fma(s_mat[idx], num, s_mat[P + idx] * den);
-                    const double dd = fma(s_mat[2 * P + idx], num, s_mat[3 * P + idx] * den);
-                    const double s = 1. / fmax(fabs(nn), fabs(dd));
-                    num = nn * s;
-                    den = dd * s;
-                }
-            }
-            __syncthreads();
-
-            // pivots inside the chunk, in the reference's order (src/Math/kwMath.cpp:32-33):
-            // gam = au[j-1] / bet;  bet = a[j] - al[j] * gam
-            double ib[M];
-            {
-                double prev = s_bin[k];
-#pragma unroll
-                for (int i = 0; i < M; ++i) {
-                    const double gam = (i ? bu[i - 1] : bu_prev) / prev;
-                    const double beta = __dsub_rn(bb[i], __dmul_rn(bl[i], gam));
-                    ib[i] = 1. / beta;
-                    prev = beta;
-                }
-            }
-            s_ib_first[k] = ib[0];
-            s_ib_last[k] = ib[M - 1];
-            __syncthreads();
-            const double ib_prev = k > 0 ? s_ib_last[k - 1] : 0.;
-            const double ib_next = k < P - 1 ? s_ib_first[k + 1] : 0.;
-#pragma unroll
-            for (int i = 0; i < M; ++i) {
-                const int j = k * M + i;
-                a[i] = -bl[i] * (i ? ib[i - 1] : ib_prev);
-                g[i] = -bu[i] * (i < M - 1 ? ib[i + 1] : ib_next);
-                D[i] = j < xDim ? 2. * ib[i] : 0.;
-            }
+            for (int c = 0; c < M2; ++c) proj2[c * P + k] = make_double2(pj[2 * c], pj[2 * c + 1]);
         }
         // spikes: Pp prefix products of a~, Q suffix products of g~, R = backward sweep of Pp
         bool bad_far = false, bad_l4 = false, bad_l3 = false, bad_l2 = false;  // "not negligible" votes

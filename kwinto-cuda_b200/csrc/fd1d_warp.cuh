@@ -1,0 +1,347 @@
+// fd1d_warp.cuh -- Layout W: one WARP per PDE, every lane owns 8*NCH contiguous nodes, the
+// time-invariant coefficient arrays live in tensor memory, the time march has no barrier.
+//
+// Same scheme and same algebra as Layout B (fd1d_reg.cuh; reference src/Math/kwFd1d.cpp:61-136 +
+// src/Math/kwMath.cpp:16-49 with the hoisted constant-dt LU in pivot-scaled unknowns), re-mapped so
+// that the FP64 pipe is fed from instruction-level parallelism instead of resident warps:
+//   * a lane's nodes are NCH chunks of 8; the chunk sweeps of one lane are independent dependent
+//     chains, so NCH of them interleave in one instruction stream;
+//   * the chunk-boundary values Yin_c / Uin_c come from an in-lane recurrence over the NCH chunks
+//     and ONE Kogge-Stone scan over the 32 lanes per direction -- the lanes are 8*NCH nodes apart,
+//     so the precomputed multipliers decay 8*NCH nodes per lane and 2-3 shuffle levels carry
+//     everything that is not provably below 2^-56 of the solution scale;
+//   * with the true incoming values known, every chunk is swept again from them ("dot + true
+//     sweep"): y_i = a_i y_{i-1} + v_i from Yin_c, u_i = g_i u_{i+1} + y_i from Uin_c,
+//     v'_i = max(D_i u_i - v_i, p_i).  Per node-step: 2 + 2 sweep DFMAs, 1 combine, 1 compare --
+//     the same 5 + 1 as Layout B's local sweeps + two fix-ups, but only a~, g~, D and p are needed,
+//     and the scans cost 16 + 2L DFMAs per PDE-step instead of 4 x 13;
+//   * a~, g~, D, p (4 x 8*NCH doubles per lane) sit in TMEM (tmem.cuh) and are streamed with
+//     tcgen05.ld in 8-double pieces right before use; v stays in registers.  No shared memory and no
+//     __syncthreads inside the march; warps of a CTA only meet for set-up and the epilogue.
+// A CTA is 4 warps = 4 PDEs (one per TMEM lane quarter); set-up of each PDE is done by all 128
+// threads with Layout B's code (setup_lu: Moebius-composed pivots in the reference's operation
+// order) and handed to the owning warp through a shared-memory stage.
+#pragma once
+#include <type_traits>
+
+#include "fd1d_reg.cuh"
+
+namespace kwfd1d {
+
+template <int NCH>
+struct WarpSmem {
+    static constexpr int N = 8 * NCH * 32;  // nodes per PDE tile
+    static constexpr int P = 32 * NCH;      // set-up threads per PDE
+    // doubles: xs[4][N] | stage a, g, D, p, v [5][N] | chunk scalars A, G, R0 [3][P] | scratch [8*P] | misc [16]
+    //          | per-warp scan constants [4][22][32]
+    static constexpr size_t bytes() { return sizeof(double) * (size_t)(4 * N + 5 * N + 3 * P + 8 * P + 16 + 4 * 22 * 32); }
+};
+
+template <int NCH, int MINB, bool ICMP>
+__global__ void __launch_bounds__(128, MINB) fd1d_warp_kernel(const Fd1dBatch B)
+{
+    static_assert(NCH == 4, "set-up is shared with Layout B's 128-thread code: 4 chunks per lane (512 < x <= 1024)");
+    using L = WarpSmem<NCH>;
+    constexpr int N = L::N;
+    constexpr int P = L::P;
+    constexpr int M = 8;
+    constexpr int NODES = 8 * NCH;  // per lane
+
+    extern __shared__ double smem[];
+    double* xs = smem;                // [4][N]
+    double* st = xs + 4 * N;          // [5][N]: a, g, D, p, v of the PDE being set up; later the final v per warp
+    double* st_A = st + 5 * N;        // [P] chunk products of a~
+    double* st_G = st_A + P;          // [P] chunk products of g~
+    double* st_R0 = st_G + P;         // [P] response of a chunk's first backward value to its Yin
+    double* scr = st_R0 + P;          // [8 * P]
+    double* misc = scr + 8 * P;       // [16] spare
+    double* wconst = misc + 16;       // [4 warps][22][32 lanes] scan constants of the warp's PDE
+
+    const int k = threadIdx.x;
+    const int lane = k & 31;
+    const int warp = k >> 5;
+    const int xDim = B.xDim;
+    const int nsteps = B.tDim - 1;
+
+    // tensor memory: 4 arrays x 8*NCH doubles per lane = 64*NCH columns per warp
+    __shared__ uint32_t s_taddr;
+    if (warp == 0) tmem::alloc<64 * NCH>(smem_addr(&s_taddr));
+    tmem::fence_before();
+    __syncthreads();
+    tmem::fence_after();
+    const uint32_t tbase = s_taddr + ((uint32_t)(warp & 3) << 21);
+    constexpr uint32_t T_A = 0, T_G = 16 * NCH, T_D = 32 * NCH, T_P = 48 * NCH;  // column offsets, 16 per chunk
+
+    const uint32_t n_pde = batch_n_pde(B);
+    const uint32_t n_grp = (n_pde + 3) / 4;
+    for (uint32_t grp = blockIdx.x; grp < n_grp; grp += gridDim.x) {
+        double vr[NODES];              // this lane's nodes of PDE 4*grp + warp
+        double Ac[NCH], Gc[NCH], R0c[NCH];
+        double bmax_mine = 1.;
+        bool put_mine = true;
+
+        // ---------------- set-up, one PDE at a time, all 128 threads ---------------------------
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t pde = 4 * grp + q;
+            if (pde >= n_pde) break;  // uniform across the CTA
+            const uint32_t rep = B.pde_rep ? __ldg(B.pde_rep + pde) : pde;
+            const kw_option opt = load_option(B.opts + rep);
+            const PdeScalars sc = pde_scalars(opt, B);
+            {
+                double v[M], pj[M], a[M], g[M], D[M];
+                setup_lu<M, P>(B, sc, ICMP ? -0. : -CUDART_INF, xs + q * N, scr, v, pj, a, g, D);
+                // chunk scalars: A = prod a~, G = prod g~, R0 = d(u~_first)/d(Yin) (backward sweep of the prefix products)
+                double Pp[M];
+                Pp[0] = a[0];
+#pragma unroll
+                for (int i = 1; i < M; ++i) Pp[i] = a[i] * Pp[i - 1];
+                double Q0 = g[M - 1], R0 = Pp[M - 1];
+#pragma unroll
+                for (int i = M - 2; i >= 0; --i) {
+                    Q0 = g[i] * Q0;
+                    R0 = fma(g[i], R0, Pp[i]);
+                }
+                double bmax = 0.;
+#pragma unroll
+                for (int i = 0; i < M; ++i) bmax = fmax(bmax, D[i] != 0. ? fabs(2. / D[i]) : 1.);
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) bmax = fmax(bmax, __shfl_xor_sync(FULL, bmax, d));
+                __syncthreads();  // setup_lu's scratch is free
+                if (lane == 0) scr[warp] = bmax;
+#pragma unroll
+                for (int i = 0; i < M; ++i) {
+                    st[0 * N + k * M + i] = a[i];
+                    st[1 * N + k * M + i] = g[i];
+                    st[2 * N + k * M + i] = D[i];
+                    st[3 * N + k * M + i] = pj[i];
+                    st[4 * N + k * M + i] = v[i];
+                }
+                st_A[k] = Pp[M - 1];
+                st_G[k] = Q0;
+                st_R0[k] = R0;
+            }
+            __syncthreads();
+            if (warp == q) {
+                // the owner pulls its lane's NCH chunks: coefficient arrays into TMEM, v into registers
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    const int ch = lane * NCH + c;
+                    double t8[8];
+#pragma unroll
+                    for (int arr = 0; arr < 4; ++arr) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) t8[i] = st[arr * N + ch * 8 + i];
+                        tmem::st8(tbase + 16 * NCH * arr + 16 * c, t8);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) vr[8 * c + i] = st[4 * N + ch * 8 + i];
+                    Ac[c] = st_A[ch];
+                    Gc[c] = st_G[ch];
+                    R0c[c] = st_R0[ch];
+                }
+                tmem::wait_st();
+                double bm = scr[0];
+#pragma unroll
+                for (int w = 1; w < 4; ++w) bm = fmax(bm, scr[w]);
+                bmax_mine = bm;
+                put_mine = sc.put;
+            }
+            __syncthreads();
+        }
+
+        const uint32_t my_pde = 4 * grp + warp;
+        const bool have = my_pde < n_pde;  // warp-uniform
+        int levels = 5;
+        if (have) {
+            // ---------------- cross-lane scan multipliers (lane aggregates) ----------------------
+            double AL = Ac[0], GL = Gc[0];
+#pragma unroll
+            for (int c = 1; c < NCH; ++c) {
+                AL *= Ac[c];
+                GL *= Gc[c];
+            }
+            double AfL[5], GbL[5];
+            {
+                double A = AL;
+#pragma unroll
+                for (int d = 0; d < 5; ++d) {
+                    const int s = 1 << d;
+                    const double o = __shfl_up_sync(FULL, A, s);
+                    AfL[d] = lane >= s ? A : 0.;
+                    if (lane >= s) A *= o;
+                }
+                double G = GL;
+#pragma unroll
+                for (int d = 0; d < 5; ++d) {
+                    const int s = 1 << d;
+                    const double o = __shfl_down_sync(FULL, G, s);
+                    GbL[d] = lane < 32 - s ? G : 0.;
+                    if (lane < 32 - s) G *= o;
+                }
+            }
+            // ---------------- how many levels carry anything (DESIGN.md "Truncation") ------------
+            {
+                const double tol = 0x1p-56 / (bmax_mine * (double)B.tDim);
+                const double* x = xs + warp * N;
+                const double x_here = fmax(0., x[min(lane * NODES, xDim - 1)]);
+                levels = 0;
+#pragma unroll
+                for (int d = 0; d < 5; ++d) {
+                    const int src = min((lane + (1 << d)) * NODES + NODES - 1, xDim - 1);
+                    const double growth = put_mine ? 1. : exp(fmax(0., x[src]) - x_here);
+                    const bool bad = !(fabs(AfL[d]) <= tol) || !(fabs(GbL[d]) * growth <= tol);
+                    if (__any_sync(FULL, bad)) levels = d + 1;
+                }
+                if (B.max_mode <= 1) levels = 5;  // FD1D.GPU.EXACT >= 1: every level
+                if (levels < 1) levels = 1;
+            }
+
+            // ---------------- time march: no barrier ---------------------------------------------
+            // The 22 per-lane scan constants are parked in shared memory ([const][lane], conflict-free)
+            // and re-read every step: registers are for v, one chunk's sweeps and the coefficient
+            // stage (current chunk + the prefetched next one).
+            double* wc = wconst + warp * (22 * 32) + lane;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                wc[(0 + c) * 32] = Ac[c];
+                wc[(4 + c) * 32] = Gc[c];
+                wc[(8 + c) * 32] = R0c[c];
+            }
+#pragma unroll
+            for (int d = 0; d < 5; ++d) {
+                wc[(12 + d) * 32] = AfL[d];
+                wc[(17 + d) * 32] = GbL[d];
+            }
+            __syncwarp();
+            const uint32_t a_wc = smem_addr(wc);
+            auto K = [&](int idx) { return lds_f64(a_wc + idx * 256); };
+
+            auto march = [&](auto lev_c) {
+                constexpr int LEV = decltype(lev_c)::value;
+                double e[NCH], f[NCH];
+                // local sweeps of chunk c from zero: e = last forward value, f = first backward value
+                auto local = [&](const double (&a8)[8], const double (&g8)[8], int c) {
+                    double y[8];
+                    y[0] = vr[8 * c];
+#pragma unroll
+                    for (int i = 1; i < 8; ++i) y[i] = fma(a8[i], y[i - 1], vr[8 * c + i]);
+                    e[c] = y[7];
+                    double u = y[7];
+#pragma unroll
+                    for (int i = 6; i >= 0; --i) u = fma(g8[i], u, y[i]);
+                    f[c] = u;
+                };
+                double an[8];  // a~ of the chunk that is processed next, always one load ahead
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    double a8[8], g8[8];
+                    tmem::ld8(tbase + T_A + 16 * c, a8);
+                    tmem::ld8(tbase + T_G + 16 * c, g8);
+                    tmem::wait_ld_dep(a8);
+                    tmem::wait_ld_dep(g8);
+                    local(a8, g8, c);
+                }
+                tmem::ld8(tbase + T_A, an);  // in flight across the scans
+                for (int step = 0; step < nsteps; ++step) {
+                    // ---- forward: lane aggregate, scan over lanes, chunk-entry values
+                    double S = e[0];
+#pragma unroll
+                    for (int c = 1; c < NCH; ++c) S = fma(K(c), S, e[c]);
+#pragma unroll
+                    for (int d = 0; d < LEV; ++d) {
+                        const double o = __shfl_up_sync(FULL, S, 1 << d);
+                        S = fma(K(12 + d), o, S);
+                    }
+                    double Yin[NCH];
+                    {
+                        const double o = __shfl_up_sync(FULL, S, 1);
+                        Yin[0] = lane ? o : 0.;
+                    }
+#pragma unroll
+                    for (int c = 1; c < NCH; ++c) Yin[c] = fma(K(c - 1), Yin[c - 1], e[c - 1]);
+                    // ---- backward: chunk-start values with the true forward carry, scan, chunk-exit values
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) f[c] = fma(K(8 + c), Yin[c], f[c]);
+                    double T = f[NCH - 1];
+#pragma unroll
+                    for (int c = NCH - 2; c >= 0; --c) T = fma(K(4 + c), T, f[c]);
+#pragma unroll
+                    for (int d = 0; d < LEV; ++d) {
+                        const double o = __shfl_down_sync(FULL, T, 1 << d);
+                        T = fma(K(17 + d), o, T);
+                    }
+                    double Uin[NCH];
+                    {
+                        const double o = __shfl_down_sync(FULL, T, 1);
+                        Uin[NCH - 1] = lane < 31 ? o : 0.;
+                    }
+#pragma unroll
+                    for (int c = NCH - 2; c >= 0; --c) Uin[c] = fma(K(4 + c + 1), Uin[c + 1], f[c + 1]);
+                    // ---- per chunk: true sweeps from (Yin, Uin), projection, next step's local sweeps;
+                    //      the next chunk's coefficients are already in flight
+                    // TMEM loads are issued one block ahead of their use: g~, D, p of this chunk and a~ of
+                    // the next arrive while the forward sweep's dependent chain runs
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) {
+                        double a8[8], g8[8], d8[8], p8[8];
+                        tmem::wait_ld_dep(an);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) a8[i] = an[i];
+                        tmem::ld8(tbase + T_G + 16 * c, g8);
+                        tmem::ld8(tbase + T_D + 16 * c, d8);
+                        tmem::ld8(tbase + T_P + 16 * c, p8);
+                        tmem::ld8(tbase + T_A + 16 * ((c + 1) & (NCH - 1)), an);
+                        double y[8];
+                        y[0] = fma(a8[0], Yin[c], vr[8 * c]);
+#pragma unroll
+                        for (int i = 1; i < 8; ++i) y[i] = fma(a8[i], y[i - 1], vr[8 * c + i]);
+                        tmem::wait_ld_dep(g8);
+                        tmem::wait_ld_dep(d8);
+                        tmem::wait_ld_dep(p8);
+                        double u = Uin[c];
+#pragma unroll
+                        for (int i = 7; i >= 0; --i) {
+                            u = fma(g8[i], u, y[i]);
+                            const double r = fma(d8[i], u, -vr[8 * c + i]);
+                            vr[8 * c + i] = ICMP ? max_like_icmp(r, p8[i]) : max_like_std(r, p8[i]);
+                        }
+                        local(a8, g8, c);
+                    }
+                }
+                tmem::wait_ld_dep(an);  // nothing in flight when the arrays are rewritten
+            };
+            switch (levels) {
+                case 1: march(std::integral_constant<int, 1>{}); break;
+                case 2: march(std::integral_constant<int, 2>{}); break;
+                case 3: march(std::integral_constant<int, 3>{}); break;
+                case 4: march(std::integral_constant<int, 4>{}); break;
+                default: march(std::integral_constant<int, 5>{}); break;
+            }
+            if (lane == 0) {
+                // histogram buckets shared with Layout B: 0 = exact requested, 1 = all 5 levels, 2/3/4 = 4/3/2, 5 = 1 level
+                const int bucket = B.max_mode == 0 ? 0 : (levels == 5 ? 1 : 6 - levels);
+                atomicAdd(&B.status[2 + bucket], 1u);
+            }
+            // ---------------- epilogue: interpolate every option of this chain -------------------
+            double* vfin = st + warp * N;  // the stage is free: set-up finished before the march
+#pragma unroll
+            for (int i = 0; i < NODES; ++i) vfin[lane * NODES + i] = vr[i];
+            __syncwarp();
+            {
+                const double* x = xs + warp * N;
+                uint32_t q0, q1;
+                chain_range(B, my_pde, q0, q1);
+                for (uint32_t q = q0 + lane; q < q1; q += 32) {
+                    const uint32_t oi = B.csr_opt ? __ldg(B.csr_opt + q) : q;
+                    price_option(B, oi, [&](int j) { return x[j]; }, [&](int j) { return vfin[j]; });
+                }
+            }
+        }
+        __syncthreads();  // stage and x grids are rewritten by the next group
+    }
+    tmem::fence_before();
+    __syncthreads();
+    if (warp == 0) tmem::dealloc<64 * NCH>(s_taddr);
+}
+
+}  // namespace kwfd1d

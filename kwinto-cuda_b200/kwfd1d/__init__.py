@@ -221,7 +221,7 @@ class Fd1dGpu_Pricer(Pricer):
         self._lib.kw_fd1d_get_info(self._h, C.byref(i))
         d = {f[0]: getattr(i, f[0]) for f in _CInfo._fields_ if f[0] != "reserved"}
         d["device_name"] = i.device_name.decode()
-        d["mode_count"] = list(i.mode_count)[:5]
+        d["mode_count"] = list(i.mode_count)[:6]
         d["layout"] = {v: k for k, v in LAYOUTS.items()}.get(i.layout, str(i.layout))
         return d
 
