@@ -54,9 +54,9 @@ struct RegVariant {
         ID, KW_FD1D_F64, 8, 128, MINB_, false, false, fd1d_reg_kernel<double, 8, 128, MINB_, false, false, ICMP_, true>, \
             RegSmem<8, 128>::bytes(false, false), 128                                              \
     }
-#define KW_VARIANT_W(ID, MINB_, ICMP_)                                                            \
+#define KW_VARIANT_W(ID, MINB_, ICMP_, PAIR_)                                                     \
     {                                                                                              \
-        ID, KW_FD1D_F64, 8, 128, MINB_, false, false, fd1d_warp_kernel<4, MINB_, ICMP_>,           \
+        ID, KW_FD1D_F64, 8, 128, MINB_, false, false, fd1d_warp_kernel<4, MINB_, ICMP_, PAIR_>,    \
             WarpSmem<4>::bytes(), 256, 4                                                           \
     }
 #define KW_VARIANT_F32(ID, M_, P_, MINB_)                                                         \
@@ -72,7 +72,7 @@ const RegVariant g_variants[] = {
     KW_VARIANT(101, 8, 64, 6, false, false),   // x <= 512
     KW_VARIANT(102, 8, 64, 8, true, true),
     KW_VARIANT(103, 8, 64, 6, true, false),
-    KW_VARIANT_W(231, 2, false),               // x <= 1024: Layout W (warp per PDE, coefficients in tensor memory)
+    KW_VARIANT_W(233, 2, false, true),              // x <= 1024: Layout W (warp per PDE, coefficients in tensor memory), chunk pairs
     KW_VARIANT(201, 8, 128, 3, false, false),  // x <= 1024, CTA per PDE (batches below one wave of Layout W)
     KW_VARIANT(202, 8, 128, 3, true, false),
     KW_VARIANT(203, 8, 128, 4, true, true),
@@ -82,7 +82,9 @@ const RegVariant g_variants[] = {
     KW_VARIANT_I(213, 8, 128, 4, true, true),
     KW_VARIANT_T(221, 4, false),  // coefficient arrays in tensor memory, 4 PDEs per SM
     KW_VARIANT_T(222, 4, true),
-    KW_VARIANT_W(232, 2, true),
+    KW_VARIANT_W(232, 2, true, false),
+    KW_VARIANT_W(231, 2, false, false),  // one chunk at a time, next chunk's a~ prefetched
+    KW_VARIANT_W(234, 2, true, true),
     KW_VARIANT(301, 8, 256, 1, false, false),  // x <= 2048
     KW_VARIANT(302, 8, 256, 2, true, true),
     KW_VARIANT(401, 8, 512, 1, true, true),    // x <= 4096

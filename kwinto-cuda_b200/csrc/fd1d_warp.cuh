@@ -26,6 +26,11 @@
 
 #include "fd1d_reg.cuh"
 
+// width of the TMEM loads in the chunk-pair phase (ld8 = one x16, ld8_by4 = two x8, ld8_by2 = four x4)
+#ifndef KW_W_LD8
+#define KW_W_LD8 tmem::ld8
+#endif
+
 namespace kwfd1d {
 
 template <int NCH>
@@ -37,7 +42,9 @@ struct WarpSmem {
     static constexpr size_t bytes() { return sizeof(double) * (size_t)(4 * N + 5 * N + 3 * P + 8 * P + 16 + 4 * 22 * 32); }
 };
 
-template <int NCH, int MINB, bool ICMP>
+// PAIR: the chunk phase processes two chunks in lock step (two interleaved dependent chains per warp)
+// instead of one chunk at a time with its coefficients prefetched.
+template <int NCH, int MINB, bool ICMP, bool PAIR = false>
 __global__ void __launch_bounds__(128, MINB) fd1d_warp_kernel(const Fd1dBatch B)
 {
     static_assert(NCH == 4, "set-up is shared with Layout B's 128-thread code: 4 chunks per lane (512 < x <= 1024)");
@@ -279,6 +286,67 @@ __global__ void __launch_bounds__(128, MINB) fd1d_warp_kernel(const Fd1dBatch B)
                     for (int c = NCH - 2; c >= 0; --c) Uin[c] = fma(K(4 + c + 1), Uin[c + 1], f[c + 1]);
                     // ---- per chunk: true sweeps from (Yin, Uin), projection, next step's local sweeps;
                     //      the next chunk's coefficients are already in flight
+                    if constexpr (PAIR) {
+#pragma unroll
+                        for (int h = 0; h < NCH; h += 2) {
+                            const int cA = h, cB = h + 1;
+                            double aA[8], aB[8], gA[8], gB[8], dA[8], dB[8], pA[8], pB[8];
+                            KW_W_LD8(tbase + T_A + 16 * cA, aA);
+                            KW_W_LD8(tbase + T_A + 16 * cB, aB);
+                            tmem::wait_ld_dep(aA);
+                            tmem::wait_ld_dep(aB);
+                            KW_W_LD8(tbase + T_G + 16 * cA, gA);
+                            KW_W_LD8(tbase + T_G + 16 * cB, gB);
+                            KW_W_LD8(tbase + T_D + 16 * cA, dA);
+                            KW_W_LD8(tbase + T_D + 16 * cB, dB);
+                            KW_W_LD8(tbase + T_P + 16 * cA, pA);
+                            KW_W_LD8(tbase + T_P + 16 * cB, pB);
+                            double yA[8], yB[8];
+                            yA[0] = fma(aA[0], Yin[cA], vr[8 * cA]);
+                            yB[0] = fma(aB[0], Yin[cB], vr[8 * cB]);
+#pragma unroll
+                            for (int i = 1; i < 8; ++i) {
+                                yA[i] = fma(aA[i], yA[i - 1], vr[8 * cA + i]);
+                                yB[i] = fma(aB[i], yB[i - 1], vr[8 * cB + i]);
+                            }
+                            tmem::wait_ld_dep(gA);
+                            tmem::wait_ld_dep(gB);
+                            tmem::wait_ld_dep(dA);
+                            tmem::wait_ld_dep(dB);
+                            tmem::wait_ld_dep(pA);
+                            tmem::wait_ld_dep(pB);
+                            double uA = Uin[cA], uB = Uin[cB];
+#pragma unroll
+                            for (int i = 7; i >= 0; --i) {
+                                uA = fma(gA[i], uA, yA[i]);
+                                uB = fma(gB[i], uB, yB[i]);
+                                const double rA = fma(dA[i], uA, -vr[8 * cA + i]);
+                                const double rB = fma(dB[i], uB, -vr[8 * cB + i]);
+                                vr[8 * cA + i] = ICMP ? max_like_icmp(rA, pA[i]) : max_like_std(rA, pA[i]);
+                                vr[8 * cB + i] = ICMP ? max_like_icmp(rB, pB[i]) : max_like_std(rB, pB[i]);
+                            }
+                            // next step's local sweeps of both chunks, interleaved
+                            yA[0] = vr[8 * cA];
+                            yB[0] = vr[8 * cB];
+#pragma unroll
+                            for (int i = 1; i < 8; ++i) {
+                                yA[i] = fma(aA[i], yA[i - 1], vr[8 * cA + i]);
+                                yB[i] = fma(aB[i], yB[i - 1], vr[8 * cB + i]);
+                            }
+                            e[cA] = yA[7];
+                            e[cB] = yB[7];
+                            uA = yA[7];
+                            uB = yB[7];
+#pragma unroll
+                            for (int i = 6; i >= 0; --i) {
+                                uA = fma(gA[i], uA, yA[i]);
+                                uB = fma(gB[i], uB, yB[i]);
+                            }
+                            f[cA] = uA;
+                            f[cB] = uB;
+                        }
+                        continue;
+                    }
                     // TMEM loads are issued one block ahead of their use: g~, D, p of this chunk and a~ of
                     // the next arrive while the forward sweep's dependent chain runs
 #pragma unroll

@@ -51,6 +51,49 @@ __device__ __forceinline__ void ld8(uint32_t taddr, double (&d)[8])
 #pragma unroll
     for (int i = 0; i < 8; ++i) d[i] = __hiloint2double((int)r[2 * i + 1], (int)r[2 * i]);
 }
+// the same 8 doubles fetched as two x8 (4 doubles) or four x4 (2 doubles) instructions: smaller
+// destination register blocks are easier to allocate next to long-lived values
+__device__ __forceinline__ void ld8_by4(uint32_t taddr, double (&d)[8])
+{
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        uint32_t r[8];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                     : "r"(taddr + 8 * h)
+                     : "memory");
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d[4 * h + i] = __hiloint2double((int)r[2 * i + 1], (int)r[2 * i]);
+    }
+}
+__device__ __forceinline__ void ld8_by2(uint32_t taddr, double (&d)[8])
+{
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+        uint32_t r[4];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                     : "r"(taddr + 4 * h)
+                     : "memory");
+        d[2 * h] = __hiloint2double((int)r[1], (int)r[0]);
+        d[2 * h + 1] = __hiloint2double((int)r[3], (int)r[2]);
+    }
+}
+// two doubles (x4) and their wait, for just-in-time operands with short live ranges
+__device__ __forceinline__ void ld2(uint32_t taddr, double& d0, double& d1)
+{
+    uint32_t r[4];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr)
+                 : "memory");
+    d0 = __hiloint2double((int)r[1], (int)r[0]);
+    d1 = __hiloint2double((int)r[3], (int)r[2]);
+}
+__device__ __forceinline__ void wait_ld_dep2(double& d0, double& d1)
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : "+d"(d0), "+d"(d1)::"memory");
+}
 __device__ __forceinline__ void st8(uint32_t taddr, const double (&d)[8])
 {
     uint32_t r[16];
