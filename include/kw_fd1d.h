@@ -171,9 +171,11 @@ int kw_fd1d_tmem_probe(int32_t device, double* out16);
 
 /* DFMA throughput (TFLOP/s) against the number of distinct REGISTER source operands:
  * out[0..3] with 16 warps per SM: one register source, two, three distinct, three with one shared by
- * consecutive instructions; out[4..7] the same with 64 warps per SM.  The march's DFMAs all read three
- * registers, so this -- not the one-register figure of kw_fd1d_fp64_peak -- is its practical ceiling. */
-int kw_fd1d_dfma_probe(int32_t device, double* out8);
+ * consecutive instructions; out[4..7] the same with 64 warps per SM; out[8], out[9]: three-source DFMAs
+ * with one / two unrelated 32-bit selects per DFMA in the same stream (16 warps per SM).  The march's
+ * DFMAs all read three registers, so this -- not the one-register figure of kw_fd1d_fp64_peak -- is its
+ * practical ceiling.  out[10]. */
+int kw_fd1d_dfma_probe(int32_t device, double* out10);
 
 const char* kw_fd1d_version(void);
 

@@ -59,6 +59,11 @@ struct RegVariant {
         ID, KW_FD1D_F64, 8, 128, MINB_, false, false, fd1d_warp_kernel<4, MINB_, ICMP_, PAIR_>,    \
             WarpSmem<4>::bytes(), 256, 4                                                           \
     }
+#define KW_VARIANT_W2(ID, MINB_, ICMP_)                                                           \
+    {                                                                                              \
+        ID, KW_FD1D_F64, 8, 128, MINB_, false, false, fd1d_warp2_kernel<4, MINB_, ICMP_>,          \
+            Warp2Smem<4>::bytes(), 256, 4                                                          \
+    }
 #define KW_VARIANT_F32(ID, M_, P_, MINB_)                                                         \
     {                                                                                              \
         ID, KW_FD1D_F32, M_, P_, MINB_, false, false, fd1d_reg_kernel<float, M_, P_, MINB_, false, false>, \
@@ -85,6 +90,8 @@ const RegVariant g_variants[] = {
     KW_VARIANT_W(232, 2, true, false),
     KW_VARIANT_W(231, 2, false, false),  // one chunk at a time, next chunk's a~ prefetched
     KW_VARIANT_W(234, 2, true, true),
+    KW_VARIANT_W2(241, 2, false),  // v in tensor memory, floor from shared memory
+    KW_VARIANT_W2(242, 2, true),
     KW_VARIANT(301, 8, 256, 1, false, false),  // x <= 2048
     KW_VARIANT(302, 8, 256, 2, true, true),
     KW_VARIANT(401, 8, 512, 1, true, true),    // x <= 4096
@@ -883,6 +890,7 @@ int kw_fd1d_tmem_probe(int32_t device, double* out16)
 int kw_fd1d_dfma_probe(int32_t device, double* out8)
 {
     if (!out8) return KW_FD1D_EINVAL;
+    for (int i = 0; i < 10; ++i) out8[i] = 0.;
     if (cudaSetDevice(device) != cudaSuccess) return KW_FD1D_ECUDA;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return KW_FD1D_ECUDA;
@@ -892,7 +900,8 @@ int kw_fd1d_dfma_probe(int32_t device, double* out8)
     for (int i = 0; i < 64; ++i) hin[i] = 1e-3 * (i + 1);
     cudaMemcpy(din, hin, sizeof hin, cudaMemcpyHostToDevice);
     typedef void (*K)(const double*, double*, int);
-    const K ks[4] = {dfma_operand_kernel<1>, dfma_operand_kernel<2>, dfma_operand_kernel<3>, dfma_operand_kernel<4>};
+    const K ks[6] = {dfma_operand_kernel<1>, dfma_operand_kernel<2>, dfma_operand_kernel<3>,
+                     dfma_operand_kernel<4>, dfma_operand_kernel<5>, dfma_operand_kernel<6>};
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
@@ -900,7 +909,8 @@ int kw_fd1d_dfma_probe(int32_t device, double* out8)
     for (int occ = 0; occ < 2; ++occ) {             // 16 and 64 warps per SM
         const int ctas = occ == 0 ? 4 : 16;
         const int grid = prop.multiProcessorCount * ctas;
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < 6; ++k) {
+            if (k >= 4 && occ == 1) continue;  // the select probes run at 16 warps per SM only
             ks[k]<<<grid, 128>>>(din, dout, 64);
             cudaEventRecord(e0);
             ks[k]<<<grid, 128>>>(din, dout, iters);
@@ -908,7 +918,7 @@ int kw_fd1d_dfma_probe(int32_t device, double* out8)
             if (cudaEventSynchronize(e1) != cudaSuccess) return KW_FD1D_ECUDA;
             float ms = 0.f;
             cudaEventElapsedTime(&ms, e0, e1);
-            out8[occ * 4 + k] = 2.0 * 32.0 * iters * (double)grid * 128 / (ms * 1e-3) * 1e-12;  // TFLOP/s
+            out8[k < 4 ? occ * 4 + k : 4 + k] = 2.0 * 32.0 * iters * (double)grid * 128 / (ms * 1e-3) * 1e-12;  // TFLOP/s
         }
     }
     cudaEventDestroy(e0);

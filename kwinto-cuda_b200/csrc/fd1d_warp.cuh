@@ -27,6 +27,12 @@
 #include "fd1d_reg.cuh"
 
 // width of the TMEM loads in the chunk-pair phase (ld8 = one x16, ld8_by4 = two x8, ld8_by2 = four x4)
+#ifndef KW_W2_ROT
+#define KW_W2_ROT 1
+#endif
+#ifndef KW_W2_ROTC
+#define KW_W2_ROTC 0
+#endif
 #ifndef KW_W_LD8
 #define KW_W_LD8 tmem::ld8
 #endif
@@ -406,6 +412,368 @@ __global__ void __launch_bounds__(128, MINB) fd1d_warp_kernel(const Fd1dBatch B)
             }
         }
         __syncthreads();  // stage and x grids are rewritten by the next group
+    }
+    tmem::fence_before();
+    __syncthreads();
+    if (warp == 0) tmem::dealloc<64 * NCH>(s_taddr);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Layout W, second arrangement: the solution v itself lives in tensor memory next to a~, g~, D
+// (read for the sweeps, written back after the projection), and the projection floor p is read from
+// shared memory two nodes at a time, just in time.  Registers then only hold what is in flight --
+// two chunks' sweeps and coefficient blocks -- which leaves the instruction scheduler room to
+// interleave the two dependent chains of a chunk pair instead of serialising them.
+// Shared memory per CTA: one x grid (set-up only; the epilogue recomputes x_j with the same
+// function), the set-up stage, one floor array per warp (re-used for the final v).
+template <int NCH>
+struct Warp2Smem {
+    static constexpr int N = 8 * NCH * 32;
+    static constexpr int P = 32 * NCH;
+    // doubles: xs[N] | stage a, g, D, p, v [5][N] (setup scratch aliases the v slot) | floors [4][N]
+    //          | chunk scalars A, G, R0 [3][P] | misc [16] | per-warp scan constants [4][22][32]
+    static constexpr size_t bytes() { return sizeof(double) * (size_t)(N + 5 * N + 4 * N + 3 * P + 16 + 4 * 22 * 32); }
+};
+
+template <int NCH, int MINB, bool ICMP>
+__global__ void __launch_bounds__(128, MINB) fd1d_warp2_kernel(const Fd1dBatch B)
+{
+    static_assert(NCH == 4, "4 chunks per lane (512 < x <= 1024)");
+    using L = Warp2Smem<NCH>;
+    constexpr int N = L::N;
+    constexpr int P = L::P;
+    constexpr int M = 8;
+    constexpr int NODES = 8 * NCH;
+
+    extern __shared__ double smem[];
+    double* xs = smem;            // [N]
+    double* st = xs + N;          // [5][N]
+    double* scr = st + 4 * N;     // setup_lu scratch = the v slot of the stage (free until staging)
+    double* ps = st + 5 * N;      // [4][N] floors, [chunk][node pair][lane] double2; after the march: final v
+    double* st_A = ps + 4 * N;    // [P]
+    double* st_G = st_A + P;
+    double* st_R0 = st_G + P;
+    double* misc = st_R0 + P;     // [0..3] per-warp bmax of the PDE being set up
+    double* wconst = misc + 16;   // [4][22][32]
+
+    const int k = threadIdx.x;
+    const int lane = k & 31;
+    const int warp = k >> 5;
+    const int xDim = B.xDim;
+    const int nsteps = B.tDim - 1;
+
+    __shared__ uint32_t s_taddr;
+    if (warp == 0) tmem::alloc<64 * NCH>(smem_addr(&s_taddr));
+    tmem::fence_before();
+    __syncthreads();
+    tmem::fence_after();
+    const uint32_t tbase = s_taddr + ((uint32_t)(warp & 3) << 21);
+    constexpr uint32_t T_A = 0, T_G = 16 * NCH, T_D = 32 * NCH, T_V = 48 * NCH;
+    // The v block is stored rotated by KW_W2_ROT doubles: a tcgen05.ld lands element j of every block in
+    // the same register bank, and a DFMA whose two block operands (a~_i and v_i, D_i and v_i) share
+    // a bank makes ptxas copy one of them elsewhere first (a third of the loop's instructions).
+#define KW_RX(isv, c, i) (((i) + KW_W2_ROTC * ((c) & 1) + ((isv) ? KW_W2_ROT : 0)) & 7)
+
+    const uint32_t n_pde = batch_n_pde(B);
+    const uint32_t n_grp = (n_pde + 3) / 4;
+    for (uint32_t grp = blockIdx.x; grp < n_grp; grp += gridDim.x) {
+        int levels = 5;
+        double* wc = wconst + warp * (22 * 32) + lane;
+        double* myp = ps + warp * N;
+
+        // ---------------- set-up, one PDE at a time, all 128 threads ---------------------------
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t pde = 4 * grp + q;
+            if (pde >= n_pde) break;  // uniform across the CTA
+            const uint32_t rep = B.pde_rep ? __ldg(B.pde_rep + pde) : pde;
+            const kw_option opt = load_option(B.opts + rep);
+            const PdeScalars sc = pde_scalars(opt, B);
+            {
+                double v[M], pj[M], a[M], g[M], D[M];
+                setup_lu<M, P>(B, sc, ICMP ? -0. : -CUDART_INF, xs, scr, v, pj, a, g, D);
+                double Pp[M];
+                Pp[0] = a[0];
+#pragma unroll
+                for (int i = 1; i < M; ++i) Pp[i] = a[i] * Pp[i - 1];
+                double Q0 = g[M - 1], R0 = Pp[M - 1];
+#pragma unroll
+                for (int i = M - 2; i >= 0; --i) {
+                    Q0 = g[i] * Q0;
+                    R0 = fma(g[i], R0, Pp[i]);
+                }
+                double bmax = 0.;
+#pragma unroll
+                for (int i = 0; i < M; ++i) bmax = fmax(bmax, D[i] != 0. ? fabs(2. / D[i]) : 1.);
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) bmax = fmax(bmax, __shfl_xor_sync(FULL, bmax, d));
+                __syncthreads();  // setup_lu's scratch (= the v slot) is free
+                if (lane == 0) misc[warp] = bmax;
+#pragma unroll
+                for (int i = 0; i < M; ++i) {
+                    st[0 * N + k * M + i] = a[i];
+                    st[1 * N + k * M + i] = g[i];
+                    st[2 * N + k * M + i] = D[i];
+                    st[3 * N + k * M + i] = pj[i];
+                    st[4 * N + k * M + i] = v[i];
+                }
+                st_A[k] = Pp[M - 1];
+                st_G[k] = Q0;
+                st_R0[k] = R0;
+            }
+            __syncthreads();
+            if (warp == q) {
+                // the owner pulls its lane's chunks: a~, g~, D, v into TMEM, the floor into its shared array
+                double Ac[NCH], Gc[NCH];
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    const int ch = lane * NCH + c;
+                    double t8[8];
+#pragma unroll
+                    for (int arr = 0; arr < 4; ++arr) {
+                        const int from = arr == 3 ? 4 : arr;  // TMEM slot 3 holds v (rotated)
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) t8[KW_RX(arr == 3, c, i)] = st[from * N + ch * 8 + i];
+                        tmem::st8(tbase + 16 * NCH * arr + 16 * c, t8);
+                    }
+#pragma unroll
+                    for (int i2 = 0; i2 < 4; ++i2)
+                        reinterpret_cast<double2*>(myp)[(c * 4 + i2) * 32 + lane] =
+                            make_double2(st[3 * N + ch * 8 + 2 * i2], st[3 * N + ch * 8 + 2 * i2 + 1]);
+                    Ac[c] = st_A[ch];
+                    Gc[c] = st_G[ch];
+                    wc[(0 + c) * 32] = Ac[c];
+                    wc[(4 + c) * 32] = Gc[c];
+                    wc[(8 + c) * 32] = st_R0[ch];
+                }
+                tmem::wait_st();
+                const double bm = fmax(fmax(misc[0], misc[1]), fmax(misc[2], misc[3]));
+                // cross-lane scan multipliers from the lane aggregates
+                double AL = Ac[0], GL = Gc[0];
+#pragma unroll
+                for (int c = 1; c < NCH; ++c) {
+                    AL *= Ac[c];
+                    GL *= Gc[c];
+                }
+                double AfL[5], GbL[5];
+                {
+                    double A = AL;
+#pragma unroll
+                    for (int d = 0; d < 5; ++d) {
+                        const int s = 1 << d;
+                        const double o = __shfl_up_sync(FULL, A, s);
+                        AfL[d] = lane >= s ? A : 0.;
+                        if (lane >= s) A *= o;
+                    }
+                    double G = GL;
+#pragma unroll
+                    for (int d = 0; d < 5; ++d) {
+                        const int s = 1 << d;
+                        const double o = __shfl_down_sync(FULL, G, s);
+                        GbL[d] = lane < 32 - s ? G : 0.;
+                        if (lane < 32 - s) G *= o;
+                    }
+                }
+#pragma unroll
+                for (int d = 0; d < 5; ++d) {
+                    wc[(12 + d) * 32] = AfL[d];
+                    wc[(17 + d) * 32] = GbL[d];
+                }
+                // how many levels carry anything (DESIGN.md "Truncation")
+                const double tol = 0x1p-56 / (bm * (double)B.tDim);
+                const double x_here = fmax(0., xs[min(lane * NODES, xDim - 1)]);
+                int lv = 0;
+#pragma unroll
+                for (int d = 0; d < 5; ++d) {
+                    const int src = min((lane + (1 << d)) * NODES + NODES - 1, xDim - 1);
+                    const double growth = sc.put ? 1. : exp(fmax(0., xs[src]) - x_here);
+                    const bool bad = !(fabs(AfL[d]) <= tol) || !(fabs(GbL[d]) * growth <= tol);
+                    if (__any_sync(FULL, bad)) lv = d + 1;
+                }
+                if (B.max_mode <= 1) lv = 5;
+                levels = lv < 1 ? 1 : lv;
+            }
+            __syncthreads();
+        }
+
+        const uint32_t my_pde = 4 * grp + warp;
+        const bool have = my_pde < n_pde;  // warp-uniform
+        if (have) {
+            const uint32_t a_wc = smem_addr(wc);
+            const uint32_t a_p = smem_addr(myp) + lane * 16;
+            auto K = [&](int idx) { return lds_f64(a_wc + idx * 256); };
+
+            auto march = [&](auto lev_c) {
+                constexpr int LEV = decltype(lev_c)::value;
+                double e[NCH], f[NCH];
+                // first local sweeps
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    double a8[8], g8[8], v8[8];
+                    tmem::ld8(tbase + T_A + 16 * c, a8);
+                    tmem::ld8(tbase + T_G + 16 * c, g8);
+                    tmem::ld8(tbase + T_V + 16 * c, v8);
+                    tmem::wait_ld_dep(a8);
+                    tmem::wait_ld_dep(g8);
+                    tmem::wait_ld_dep(v8);
+                    double y[8];
+                    y[0] = v8[KW_RX(1, c, 0)];
+#pragma unroll
+                    for (int i = 1; i < 8; ++i) y[i] = fma(a8[KW_RX(0, c, i)], y[i - 1], v8[KW_RX(1, c, i)]);
+                    e[c] = y[7];
+                    double u = y[7];
+#pragma unroll
+                    for (int i = 6; i >= 0; --i) u = fma(g8[KW_RX(0, c, i)], u, y[i]);
+                    f[c] = u;
+                }
+                for (int step = 0; step < nsteps; ++step) {
+                    // ---- forward: lane aggregate, scan over lanes, chunk-entry values
+                    double S = e[0];
+#pragma unroll
+                    for (int c = 1; c < NCH; ++c) S = fma(K(c), S, e[c]);
+#pragma unroll
+                    for (int d = 0; d < LEV; ++d) {
+                        const double o = __shfl_up_sync(FULL, S, 1 << d);
+                        S = fma(K(12 + d), o, S);
+                    }
+                    double Yin[NCH];
+                    {
+                        const double o = __shfl_up_sync(FULL, S, 1);
+                        Yin[0] = lane ? o : 0.;
+                    }
+#pragma unroll
+                    for (int c = 1; c < NCH; ++c) Yin[c] = fma(K(c - 1), Yin[c - 1], e[c - 1]);
+                    // ---- backward
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) f[c] = fma(K(8 + c), Yin[c], f[c]);
+                    double T = f[NCH - 1];
+#pragma unroll
+                    for (int c = NCH - 2; c >= 0; --c) T = fma(K(4 + c), T, f[c]);
+#pragma unroll
+                    for (int d = 0; d < LEV; ++d) {
+                        const double o = __shfl_down_sync(FULL, T, 1 << d);
+                        T = fma(K(17 + d), o, T);
+                    }
+                    double Uin[NCH];
+                    {
+                        const double o = __shfl_down_sync(FULL, T, 1);
+                        Uin[NCH - 1] = lane < 31 ? o : 0.;
+                    }
+#pragma unroll
+                    for (int c = NCH - 2; c >= 0; --c) Uin[c] = fma(K(4 + c + 1), Uin[c + 1], f[c + 1]);
+                    tmem::wait_st();  // last step's v is in place
+                    // ---- chunk pairs: true sweeps from (Yin, Uin), projection, v back to TMEM, next local sweeps
+#pragma unroll
+                    for (int h = 0; h < NCH; h += 2) {
+                        const int cA = h, cB = h + 1;
+                        double aA[8], aB[8], vA[8], vB[8], gA[8], gB[8], dA[8], dB[8];
+                        tmem::ld8(tbase + T_A + 16 * cA, aA);
+                        tmem::ld8(tbase + T_A + 16 * cB, aB);
+                        tmem::ld8(tbase + T_V + 16 * cA, vA);
+                        tmem::ld8(tbase + T_V + 16 * cB, vB);
+                        tmem::wait_ld_dep(aA);
+                        tmem::wait_ld_dep(aB);
+                        tmem::wait_ld_dep(vA);
+                        tmem::wait_ld_dep(vB);
+                        tmem::ld8(tbase + T_G + 16 * cA, gA);
+                        tmem::ld8(tbase + T_G + 16 * cB, gB);
+                        tmem::ld8(tbase + T_D + 16 * cA, dA);
+                        tmem::ld8(tbase + T_D + 16 * cB, dB);
+                        double yA[8], yB[8];
+                        yA[0] = fma(aA[KW_RX(0, cA, 0)], Yin[cA], vA[KW_RX(1, cA, 0)]);
+                        yB[0] = fma(aB[KW_RX(0, cB, 0)], Yin[cB], vB[KW_RX(1, cB, 0)]);
+#pragma unroll
+                        for (int i = 1; i < 8; ++i) {
+                            yA[i] = fma(aA[KW_RX(0, cA, i)], yA[i - 1], vA[KW_RX(1, cA, i)]);
+                            yB[i] = fma(aB[KW_RX(0, cB, i)], yB[i - 1], vB[KW_RX(1, cB, i)]);
+                        }
+                        tmem::wait_ld_dep(gA);
+                        tmem::wait_ld_dep(gB);
+                        tmem::wait_ld_dep(dA);
+                        tmem::wait_ld_dep(dB);
+                        double uA = Uin[cA], uB = Uin[cB];
+#pragma unroll
+                        for (int i2 = 3; i2 >= 0; --i2) {
+                            const double2 pA = lds_v2f64(a_p + (cA * 4 + i2) * 512);
+                            const double2 pB = lds_v2f64(a_p + (cB * 4 + i2) * 512);
+                            {
+                                const int i = 2 * i2 + 1;
+                                uA = fma(gA[KW_RX(0, cA, i)], uA, yA[i]);
+                                uB = fma(gB[KW_RX(0, cB, i)], uB, yB[i]);
+                                const double rA = fma(dA[KW_RX(0, cA, i)], uA, -vA[KW_RX(1, cA, i)]);
+                                const double rB = fma(dB[KW_RX(0, cB, i)], uB, -vB[KW_RX(1, cB, i)]);
+                                vA[KW_RX(1, cA, i)] = ICMP ? max_like_icmp(rA, pA.y) : max_like_std(rA, pA.y);
+                                vB[KW_RX(1, cB, i)] = ICMP ? max_like_icmp(rB, pB.y) : max_like_std(rB, pB.y);
+                            }
+                            {
+                                const int i = 2 * i2;
+                                uA = fma(gA[KW_RX(0, cA, i)], uA, yA[i]);
+                                uB = fma(gB[KW_RX(0, cB, i)], uB, yB[i]);
+                                const double rA = fma(dA[KW_RX(0, cA, i)], uA, -vA[KW_RX(1, cA, i)]);
+                                const double rB = fma(dB[KW_RX(0, cB, i)], uB, -vB[KW_RX(1, cB, i)]);
+                                vA[KW_RX(1, cA, i)] = ICMP ? max_like_icmp(rA, pA.x) : max_like_std(rA, pA.x);
+                                vB[KW_RX(1, cB, i)] = ICMP ? max_like_icmp(rB, pB.x) : max_like_std(rB, pB.x);
+                            }
+                        }
+                        tmem::st8(tbase + T_V + 16 * cA, vA);
+                        tmem::st8(tbase + T_V + 16 * cB, vB);
+                        // next step's local sweeps of both chunks
+                        yA[0] = vA[KW_RX(1, cA, 0)];
+                        yB[0] = vB[KW_RX(1, cB, 0)];
+#pragma unroll
+                        for (int i = 1; i < 8; ++i) {
+                            yA[i] = fma(aA[KW_RX(0, cA, i)], yA[i - 1], vA[KW_RX(1, cA, i)]);
+                            yB[i] = fma(aB[KW_RX(0, cB, i)], yB[i - 1], vB[KW_RX(1, cB, i)]);
+                        }
+                        e[cA] = yA[7];
+                        e[cB] = yB[7];
+                        uA = yA[7];
+                        uB = yB[7];
+#pragma unroll
+                        for (int i = 6; i >= 0; --i) {
+                            uA = fma(gA[KW_RX(0, cA, i)], uA, yA[i]);
+                            uB = fma(gB[KW_RX(0, cB, i)], uB, yB[i]);
+                        }
+                        f[cA] = uA;
+                        f[cB] = uB;
+                    }
+                }
+                tmem::wait_st();
+            };
+            switch (levels) {
+                case 1: march(std::integral_constant<int, 1>{}); break;
+                case 2: march(std::integral_constant<int, 2>{}); break;
+                case 3: march(std::integral_constant<int, 3>{}); break;
+                case 4: march(std::integral_constant<int, 4>{}); break;
+                default: march(std::integral_constant<int, 5>{}); break;
+            }
+            if (lane == 0) {
+                const int bucket = B.max_mode == 0 ? 0 : (levels == 5 ? 1 : 6 - levels);
+                atomicAdd(&B.status[2 + bucket], 1u);
+            }
+            // ---------------- epilogue: final v out of TMEM, x_j recomputed, interpolate -----------
+            double* vfin = myp;  // the floors are not needed any more
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                double v8[8];
+                tmem::ld8(tbase + T_V + 16 * c, v8);
+                tmem::wait_ld_dep(v8);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) vfin[lane * NODES + 8 * c + i] = v8[KW_RX(1, c, i)];
+            }
+            __syncwarp();
+            {
+                const uint32_t rep = B.pde_rep ? __ldg(B.pde_rep + my_pde) : my_pde;
+                const PdeScalars sc = pde_scalars(load_option(B.opts + rep), B);
+                uint32_t q0, q1;
+                chain_range(B, my_pde, q0, q1);
+                for (uint32_t q = q0 + lane; q < q1; q += 32) {
+                    const uint32_t oi = B.csr_opt ? __ldg(B.csr_opt + q) : q;
+                    price_option(B, oi, [&](int j) { return x_node(sc, B.density, j); }, [&](int j) { return vfin[j]; });
+                }
+            }
+        }
+        __syncthreads();
     }
     tmem::fence_before();
     __syncthreads();

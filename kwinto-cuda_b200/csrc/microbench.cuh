@@ -227,6 +227,12 @@ __global__ void __launch_bounds__(128) dfma_operand_kernel(const double* in, dou
         acc[i] = in[(threadIdx.x + 16 + i) & 63];
     }
     const double Y = in[blockIdx.x & 63];
+    int s0[8], s1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        s0[i] = (int)threadIdx.x + i;
+        s1[i] = (int)blockIdx.x - i;
+    }
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -236,12 +242,19 @@ __global__ void __launch_bounds__(128) dfma_operand_kernel(const double* in, dou
                 if (KIND == 2) acc[i] = fma(x[i], 1e-9, acc[i]);
                 if (KIND == 3) acc[i] = fma(x[i], y[i], acc[i]);
                 if (KIND == 4) acc[i] = fma(x[i], Y, acc[i]);
+                if (KIND == 5 || KIND == 6) {
+                    // three-source DFMA plus one (5) or two (6) 32-bit integer ops on unrelated registers:
+                    // do non-FP64 instructions that read registers slow the FP64 stream down?
+                    acc[i] = fma(x[i], y[i], acc[i]);
+                    s0[i] = s0[i] + s1[(i + 1) & 7];          // IADD3, two register sources
+                    if (KIND == 6) s1[i] = s1[i] ^ s0[(i + 3) & 7];  // LOP3, two register sources
+                }
             }
         }
     }
     double s = 0.;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s += acc[i];
+    for (int i = 0; i < 8; ++i) s += acc[i] + (double)(s0[i] ^ s1[i]);
     if (s == 12345.678) out[0] = s;
 }
 }  // namespace kwfd1d

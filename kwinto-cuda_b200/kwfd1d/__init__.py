@@ -303,8 +303,11 @@ def tmem_probe(device: int = 0) -> dict:
 def dfma_probe(device: int = 0) -> dict:
     """DFMA TFLOP/s by number of distinct register source operands, at 16 and 64 warps per SM."""
     L = load_library()
-    out = (C.c_double * 8)()
+    out = (C.c_double * 10)()
     if L.kw_fd1d_dfma_probe(device, out) != KW_FD1D_OK:
         raise RuntimeError("kw_fd1d_dfma_probe failed (no CUDA device?)")
     names = ["1reg", "2reg", "3reg", "3reg_shared"]
-    return {f"{n}_{w}warps": out[i * 4 + j] for i, w in enumerate((16, 64)) for j, n in enumerate(names)}
+    res = {f"{n}_{w}warps": out[i * 4 + j] for i, w in enumerate((16, 64)) for j, n in enumerate(names)}
+    res["3reg_plus_1sel_16warps"] = out[8]
+    res["3reg_plus_2sel_16warps"] = out[9]
+    return res

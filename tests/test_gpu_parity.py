@@ -91,7 +91,7 @@ def test_layouts_agree_with_reference(layout):
         assert maxdiff(got, g[k + "/fd1d"]) <= TOL, (layout, k)
 
 
-@pytest.mark.parametrize("variant", [201, 202, 203, 204, 205, 211, 213, 221, 222, 231, 232, 233, 234])
+@pytest.mark.parametrize("variant", [201, 202, 203, 204, 205, 211, 213, 221, 222, 231, 232, 233, 234, 241, 242])
 def test_all_1024_variants(variant):
     g, _ = synthetic_cases()
     p = make_pricer(1024, 1024, **{"FD1D.GPU.VARIANT": variant})
@@ -142,7 +142,7 @@ def test_device_side_compression_matches_host_side():
     assert err == "" and np.array_equal(pa, pb)
 
 
-@pytest.mark.parametrize("variant", [221, 222, 231, 232, 233, 234])
+@pytest.mark.parametrize("variant", [221, 222, 231, 232, 233, 234, 241, 242])
 def test_tmem_variants_all_modes_and_reuse(variant, oracle):
     """Tensor-memory variants: every carry mode (forced through FD1D.GPU.EXACT), more PDEs than resident
     CTAs (the TMEM arrays are rewritten per PDE), mixed calls/puts/Europeans, non-multiple-of-8 grid."""
