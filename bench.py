@@ -37,7 +37,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=32768, help="options per GPU per step")
+    ap.add_argument("--n", "--options-per-gpu", dest="n", type=int, default=32768,
+                    help="options per GPU per step (use the long form under torchrun, whose parser claims --n)")
     ap.add_argument("--x", type=int, default=1024)
     ap.add_argument("--t", type=int, default=1024)
     ap.add_argument("--seed", type=int, default=42)
@@ -298,6 +299,10 @@ def main():
             peak_meas, mhz_eff = kwfd1d.fp64_peak(local_rank)
         except Exception:
             peak_meas, mhz_eff = None, None
+        try:
+            probe = kwfd1d.dfma_probe(local_rank)
+        except Exception:
+            probe = None
         sm_max = (clocks or {}).get("sm_max_mhz") or 1965.0
         try:
             mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -322,6 +327,11 @@ def main():
             "peak_nominal": peak_nominal, "frac_nominal": achieved / peak_nominal,
             "algorithmic_bytes_per_option": 64,
         }
+        if probe:
+            # every DFMA of the march reads three distinct registers; such DFMAs issue every 3 cycles, not 2
+            # (DESIGN.md "Roofline"): the measured ceiling for this instruction form, reported next to the peak
+            roofline["peak_3source_dfma"] = probe["3reg_64warps"]
+            roofline["frac_of_3source_dfma_peak"] = achieved / probe["3reg_64warps"]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
