@@ -18,6 +18,7 @@
 #include "fd1d_reg.cuh"
 #include "fd1d_soa.cuh"
 #include "fd1d_warp.cuh"
+#include "fd1d_wide.cuh"
 #include "compress.cuh"
 #include "microbench.cuh"
 
@@ -27,6 +28,8 @@ namespace {
 
 // ---------------------------------------------------------------- variants of Layout B
 typedef void (*RegKernel)(const Fd1dBatch);
+typedef void (*WideSetup)(const Fd1dBatch, double*, uint32_t, uint32_t, int);
+typedef void (*WideMarch)(const Fd1dBatch, const double*, uint32_t, uint32_t);
 struct RegVariant {
     int id;        // 100*log2(P/32) + serial (+1000 for the fp32 march); see the table
     int prec;      // KW_FD1D_F64 / KW_FD1D_F32
@@ -36,6 +39,13 @@ struct RegVariant {
     size_t smem;
     int tmem_cols;  // tensor-memory columns each CTA allocates (0 = none)
     int pdes_per_cta;  // 0/1: one PDE per CTA (Layout B); 4: one PDE per warp (Layout W)
+    // wide Layout W (fd1d_wide.cuh): NWP warps per PDE, set-up in a kernel of its own through an HBM workspace
+    int wide_nwp;
+    WideSetup setup_fn;
+    WideMarch wide_fn;
+    size_t setup_smem;
+    size_t slot_doubles;
+    int icmp;
 };
 
 #define KW_VARIANT(ID, M_, P_, MINB_, PJ_, DQ_)                                                   \
@@ -63,6 +73,12 @@ struct RegVariant {
     {                                                                                              \
         ID, KW_FD1D_F64, 8, 128, MINB_, false, false, fd1d_warp2_kernel<4, MINB_, ICMP_>,          \
             Warp2Smem<4>::bytes(), 256, 4                                                          \
+    }
+#define KW_VARIANT_WIDE(ID, NWP_, ICMP_)                                                          \
+    {                                                                                              \
+        ID, KW_FD1D_F64, 8, 128 * NWP_, 2, false, false, nullptr, WideSmem<NWP_>::bytes(), 256,    \
+            4 / NWP_, NWP_, fd1d_wide_setup_kernel<128 * NWP_>, fd1d_wide_kernel<NWP_, 2, ICMP_>,  \
+            sizeof(double) * 16 * 128 * NWP_, WideSlot<128 * NWP_>::doubles, ICMP_                 \
     }
 #define KW_VARIANT_F32(ID, M_, P_, MINB_)                                                         \
     {                                                                                              \
@@ -92,9 +108,11 @@ const RegVariant g_variants[] = {
     KW_VARIANT_W(234, 2, true, true),
     KW_VARIANT_W2(241, 2, false),  // v in tensor memory, floor from shared memory
     KW_VARIANT_W2(242, 2, true),
-    KW_VARIANT(301, 8, 256, 1, false, false),  // x <= 2048
+    KW_VARIANT_WIDE(331, 2, false),            // x <= 2048: Layout W over two warps per PDE
+    KW_VARIANT(301, 8, 256, 1, false, false),  // x <= 2048, CTA per PDE (small batches)
     KW_VARIANT(302, 8, 256, 2, true, true),
-    KW_VARIANT(401, 8, 512, 1, true, true),    // x <= 4096
+    KW_VARIANT_WIDE(431, 4, false),            // x <= 4096: Layout W over four warps per PDE
+    KW_VARIANT(401, 8, 512, 1, true, true),    // x <= 4096, CTA per PDE (small batches)
     KW_VARIANT(402, 8, 512, 1, true, false),
     // fp32 march (fp64 set-up): FD1D.GPU.PRECISION = f32
     KW_VARIANT_F32(1001, 8, 32, 16),
@@ -259,6 +277,7 @@ struct kw_fd1d_handle {
     DevBuf<kw_option> d_opts, d_opts2;
     DevBuf<double> d_prices, d_prices2;
     DevBuf<uint32_t> d_rep, d_start, d_csr;
+    DevBuf<double> d_ws;       // wide Layout W: set-up workspace for one chunk of the batch
     DevBuf<uint32_t> d_chain;  // device-side compression: one slab carved into the ChainTable arrays
     bool dev_compressed = false;
     DevBuf<unsigned int> d_status;
@@ -308,6 +327,27 @@ int launch_batch(kw_fd1d_handle* h, Fd1dBatch B, cudaStream_t st)
         const uint32_t want = (B.n_pde + ppc - 1) / ppc;  // with device-side compression n_pde = n is an upper bound
         if ((uint32_t)grid > want) grid = (int)want;
         h->last_grid = grid;
+        if (v->wide_nwp) {
+            // set-up kernel -> HBM workspace -> march kernel, one chunk of the batch at a time
+            const uint32_t cap = std::min<uint32_t>(B.n_pde, 2048u);
+            KW_CUDA(h, h->d_ws.reserve((size_t)cap * v->slot_doubles));
+            KW_CUDA(h, cudaEventRecord(h->ev0, st));
+            const int P = 128 * v->wide_nwp;
+            for (uint32_t base = 0; base < B.n_pde; base += cap) {
+                const uint32_t cnt = std::min<uint32_t>(cap, B.n_pde - base);
+                const int gs = (int)std::min<uint32_t>(cnt, (uint32_t)(h->sm_count * (2048 / P)));
+                v->setup_fn<<<gs, P, v->setup_smem, st>>>(B, h->d_ws.p, base, cnt, v->icmp);
+                const uint32_t wantc = (cnt + ppc - 1) / ppc;
+                const int gm = (int)std::min<uint32_t>(wantc, (uint32_t)(h->sm_count * h->ctas_per_sm));
+                v->wide_fn<<<gm, 128, v->smem, st>>>(B, h->d_ws.p, base, cnt);
+                h->launches += 2;
+                h->last_grid = gm;
+            }
+            KW_CUDA(h, cudaEventRecord(h->ev1, st));
+            h->ev_valid = true;
+            KW_CUDA(h, cudaGetLastError());
+            return KW_FD1D_OK;
+        }
         KW_CUDA(h, cudaEventRecord(h->ev0, st));
         v->fn<<<grid, v->P, v->smem, st>>>(B);
         h->launches += 1;
@@ -497,6 +537,19 @@ int check_status(kw_fd1d_handle* h, cudaStream_t st, const kw_option* host_asset
 // occupancy and attributes of one kernel variant
 int prepare_variant(kw_fd1d_handle* h, const RegVariant* var, const cudaDeviceProp& prop, int& ctas_per_sm, int& regs)
 {
+    if (var->wide_nwp) {
+        KW_CUDA(h, cudaFuncSetAttribute(var->setup_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)var->setup_smem));
+        KW_CUDA(h, cudaFuncSetAttribute(var->wide_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)var->smem));
+        KW_CUDA(h, cudaFuncSetAttribute(var->wide_fn, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                        cudaSharedmemCarveoutMaxShared));
+        cudaFuncAttributes fa;
+        KW_CUDA(h, cudaFuncGetAttributes(&fa, var->wide_fn));
+        regs = fa.numRegs;
+        const int by_regs = 65536 / (fa.numRegs * 128);
+        const int by_smem = (int)((size_t)prop.sharedMemPerMultiprocessor / (var->smem + 1024));
+        ctas_per_sm = std::max(1, std::min({by_regs, by_smem, 512 / var->tmem_cols, var->minb}));
+        return KW_FD1D_OK;
+    }
     KW_CUDA(h, cudaFuncSetAttribute(var->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)var->smem));
     cudaFuncAttributes fa;
     KW_CUDA(h, cudaFuncGetAttributes(&fa, var->fn));
@@ -528,7 +581,7 @@ const RegVariant* find_small_variant(int xDim, int prec)
     const RegVariant* best = nullptr;
     for (int i = 0; i < kNumVariants; ++i) {
         const RegVariant& v = g_variants[i];
-        if (v.M * v.P < xDim || v.prec != prec || v.pdes_per_cta > 1 || v.tmem_cols > 0) continue;
+        if (v.M * v.P < xDim || v.prec != prec || v.pdes_per_cta > 1 || v.tmem_cols > 0 || v.wide_nwp) continue;
         if (!best || v.P < best->P) best = &v;
     }
     return best;
@@ -594,13 +647,13 @@ int kw_fd1d_create(const kw_fd1d_config* cfg, kw_fd1d_handle** out)
         if (!h->var)
             return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::init: no register-layout kernel variant for this FD1D.X_GRID_SIZE / FD1D.GPU.VARIANT");
         if (int rc = prepare_variant(h, h->var, prop, h->ctas_per_sm, h->regs)) return rc;
-        if (cfg->variant == 0 && h->var->pdes_per_cta > 1) {
+        if (cfg->variant == 0 && (h->var->pdes_per_cta > 1 || h->var->wide_nwp)) {
             // Layout W packs 4 PDEs into a CTA and 8 into an SM: below one full wave of the device the
             // CTA-per-PDE kernel spreads the batch over more SMs (DESIGN.md "dispatch")
             h->var_small = find_small_variant((int)cfg->x_grid_size, cfg->precision);
             if (h->var_small) {
                 if (int rc = prepare_variant(h, h->var_small, prop, h->ctas_per_sm_small, h->regs_small)) return rc;
-                h->small_below = (uint32_t)(h->sm_count * h->ctas_per_sm * h->var->pdes_per_cta);
+                h->small_below = (uint32_t)(h->sm_count * h->ctas_per_sm * std::max(1, h->var->pdes_per_cta));
             }
         }
     } else if (layout == KW_FD1D_LAYOUT_SOA) {
@@ -637,6 +690,7 @@ void kw_fd1d_destroy(kw_fd1d_handle* h)
     h->d_start.release();
     h->d_csr.release();
     h->d_chain.release();
+    h->d_ws.release();
     h->d_status.release();
     h->d_soa.release();
     h->h_idx.release();
@@ -761,8 +815,9 @@ int kw_fd1d_get_info(const kw_fd1d_handle* hc, kw_fd1d_info* info)
     const RegVariant* lv = h->last_var ? h->last_var : h->var;
     const bool lsmall = lv && lv == h->var_small;
     info->variant = lv ? lv->id : 0;
-    info->threads_per_pde = lv ? (lv->pdes_per_cta > 1 ? 32 : lv->P) : 1;
-    info->nodes_per_thread = lv ? (lv->pdes_per_cta > 1 ? lv->M * lv->pdes_per_cta : lv->M) : (int)h->cfg.x_grid_size;
+    const bool lw = lv && (lv->pdes_per_cta > 1 || lv->wide_nwp);  // Layout W: 32 nodes per lane
+    info->threads_per_pde = lv ? (lv->wide_nwp ? 32 * lv->wide_nwp : (lw ? 32 : lv->P)) : 1;
+    info->nodes_per_thread = lv ? (lw ? 32 : lv->M) : (int)h->cfg.x_grid_size;
     info->ctas_per_sm = lsmall ? h->ctas_per_sm_small : h->ctas_per_sm;
     info->regs_per_thread = lsmall ? h->regs_small : h->regs;
     info->smem_per_cta = lv ? (int)lv->smem : 0;
