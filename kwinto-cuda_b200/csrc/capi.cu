@@ -329,7 +329,11 @@ int launch_batch(kw_fd1d_handle* h, Fd1dBatch B, cudaStream_t st)
         h->last_grid = grid;
         if (v->wide_nwp) {
             // set-up kernel -> HBM workspace -> march kernel, one chunk of the batch at a time
-            const uint32_t cap = std::min<uint32_t>(B.n_pde, 2048u);
+            // chunk = as many PDEs as fit a 2 GiB workspace (a multiple of one wave of the march grid)
+            const uint32_t wave = (uint32_t)(h->sm_count * h->ctas_per_sm) * ppc;
+            uint32_t fit = (uint32_t)(((size_t)2 << 30) / (v->slot_doubles * sizeof(double)));
+            fit = std::max(wave, fit / wave * wave);
+            const uint32_t cap = std::min<uint32_t>(B.n_pde, fit);
             KW_CUDA(h, h->d_ws.reserve((size_t)cap * v->slot_doubles));
             KW_CUDA(h, cudaEventRecord(h->ev0, st));
             const int P = 128 * v->wide_nwp;

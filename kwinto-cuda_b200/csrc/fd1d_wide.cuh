@@ -16,7 +16,11 @@
 //     4096), which the march kernel reads once.  Against 4095 time steps that round trip is 0.3 % of the
 //     march's time; the workspace is sized for a chunk of the batch and reused.
 // Replaces the 512-thread CTA-per-PDE kernel of Layout B for these sizes (one resident PDE per SM,
-// sixteen warps in lock step at one barrier: 16 % of FP64 peak at 4096^2).
+// sixteen warps in lock step at one barrier: 16 % of FP64 peak at 4096^2; this kernel: 32 %).
+// The step is ~540 instructions, more than the ~512 a sub-partition's instruction cache seems to hold
+// (ncu: stall_no_instruction).  A compact variant (v in TMEM, floor and e/f/Yin/Uin in shared memory,
+// the chunk-pair phase as a real loop: 310 instructions) removed those stalls and lost 15-20 % to the
+// extra shared-memory traffic (60 % of the smem pipe), so the unrolled form stays.
 #pragma once
 #include "fd1d_warp.cuh"
 
@@ -95,8 +99,9 @@ template <int NWP>
 struct WideSmem {
     static constexpr int PPC = 4 / NWP;         // PDEs per CTA
     static constexpr int N = 1024 * NWP;        // nodes per PDE tile
-    // doubles: final v [PPC][N] | per-warp scan constants [4][24][32] | exchange: Zf, Zb [2 parities][4] , AWf, AWb [4]
-    static constexpr size_t bytes() { return sizeof(double) * (size_t)(PPC * N + 4 * 24 * 32 + 2 * 2 * 4 + 2 * 4 + 8); }
+    // doubles: final v [PPC][N] | per-warp scan constants [4][24][32] | exchange: Zf, Zb [2 parities][4], AWf, AWb [4]
+    //          | carry rows cf, cb [4 warps][4]
+    static constexpr size_t bytes() { return sizeof(double) * (size_t)(PPC * N + 4 * 24 * 32 + 2 * 2 * 4 + 2 * 4 + 2 * 16 + 8); }
 };
 
 // named barrier of one PDE's warps; the id is an immediate so that only the barriers in use are reserved
@@ -128,6 +133,8 @@ __global__ void __launch_bounds__(128, MINB) fd1d_wide_kernel(const Fd1dBatch B,
     double* zb = zf + 8;                           // [2][4]
     double* awf = zb + 8;                          // [4]
     double* awb = awf + 4;                         // [4]
+    double* cfr = awb + 4;                         // [4 warps][4]: X_w  = sum_w' cf[w][w'] Zf[w']
+    double* cbr = cfr + 16;                        // [4 warps][4]: Xb_w = sum_w' cb[w][w'] Zb[w']
 
     const int k = threadIdx.x;
     const int lane = k & 31;
@@ -251,9 +258,35 @@ __global__ void __launch_bounds__(128, MINB) fd1d_wide_kernel(const Fd1dBatch B,
                 // code path, but a common value keeps the histogram per PDE
             }
             group_barrier<32 * NWP>(grp);  // awf / awb visible to the PDE's warps
+            if (lane == 0) {
+                // X_w = Z_{w-1} + AW_{w-1} X_{w-1} unrolled into one row of weights per warp (0 outside the PDE
+                // or on the wrong side), so that the march evaluates its carry as a branch-free dot product
+                double c = 1.;
+                for (int w = 3; w >= 0; --w) {
+                    double val = 0.;
+                    if (w >= w0 && w < warp) {
+                        val = c;
+                        c *= awf[w];
+                    }
+                    cfr[warp * 4 + w] = val;
+                }
+                c = 1.;
+                for (int w = 0; w < 4; ++w) {
+                    double val = 0.;
+                    if (w > warp && w < w0 + NWP) {
+                        val = c;
+                        c *= awb[w];
+                    }
+                    cbr[warp * 4 + w] = val;
+                }
+            }
+            __syncwarp();
             const uint32_t a_wc = smem_addr(wc);
             auto K = [&](int idx2) { return lds_f64(a_wc + idx2 * 256); };
-            const uint32_t a_zf = smem_addr(zf), a_zb = smem_addr(zb), a_awf = smem_addr(awf), a_awb = smem_addr(awb);
+            const uint32_t a_zf = smem_addr(zf), a_zb = smem_addr(zb);
+            const uint32_t a_cf = smem_addr(cfr + warp * 4), a_cb = smem_addr(cbr + warp * 4);
+            const uint32_t a_myzf = a_zf + warp * 8, a_myzb = a_zb + warp * 8;
+            const bool last_lane = lane == 31, first_lane = lane == 0;
 
             auto march = [&](auto lev_c) {
                 constexpr int LEV = decltype(lev_c)::value;
@@ -286,14 +319,13 @@ __global__ void __launch_bounds__(128, MINB) fd1d_wide_kernel(const Fd1dBatch B,
                         const double o = __shfl_up_sync(FULL, S, 1 << d);
                         S = fma(K(12 + d), o, S);
                     }
-                    if (lane == 31) sts_f64(a_zf + par + warp * 8, S);
+                    if (last_lane) sts_f64(a_myzf + par, S);
                     double Sm1 = __shfl_up_sync(FULL, S, 1);
-                    if (lane == 0) Sm1 = 0.;
+                    if (first_lane) Sm1 = 0.;
                     group_barrier<32 * NWP>(grp);
                     double X = 0.;
 #pragma unroll
-                    for (int w = 0; w < NWP - 1; ++w)
-                        if (w < wq) X = fma(lds_f64(a_awf + (w0 + w) * 8), X, lds_f64(a_zf + par + (w0 + w) * 8));
+                    for (int w = 0; w < 4; ++w) X = fma(lds_f64(a_cf + w * 8), lds_f64(a_zf + par + w * 8), X);
                     double Yin[NCH];
                     Yin[0] = fma(K(22), X, Sm1);
 #pragma unroll
@@ -309,14 +341,13 @@ __global__ void __launch_bounds__(128, MINB) fd1d_wide_kernel(const Fd1dBatch B,
                         const double o = __shfl_down_sync(FULL, T, 1 << d);
                         T = fma(K(17 + d), o, T);
                     }
-                    if (lane == 0) sts_f64(a_zb + par + warp * 8, T);
+                    if (first_lane) sts_f64(a_myzb + par, T);
                     double Tp1 = __shfl_down_sync(FULL, T, 1);
-                    if (lane == 31) Tp1 = 0.;
+                    if (last_lane) Tp1 = 0.;
                     group_barrier<32 * NWP>(grp);
                     double Xb = 0.;
 #pragma unroll
-                    for (int w = NWP - 1; w >= 1; --w)
-                        if (w > wq) Xb = fma(lds_f64(a_awb + (w0 + w) * 8), Xb, lds_f64(a_zb + par + (w0 + w) * 8));
+                    for (int w = 0; w < 4; ++w) Xb = fma(lds_f64(a_cb + w * 8), lds_f64(a_zb + par + w * 8), Xb);
                     double Uin[NCH];
                     Uin[NCH - 1] = fma(K(23), Xb, Tp1);
 #pragma unroll

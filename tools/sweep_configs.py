@@ -48,7 +48,7 @@ def main():
     ap.add_argument("--configs", default="3,4,5")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--n4", type=int, default=1 << 20)
-    ap.add_argument("--n5", type=int, default=2048)
+    ap.add_argument("--n5", type=int, default=8192)
     a = ap.parse_args()
     peak, mhz = kwfd1d.fp64_peak(0)
     print(f"measured FP64 peak {peak:.2f} TFLOP/s ({mhz:.0f} MHz effective)\n")
