@@ -353,7 +353,7 @@ int launch_batch(kw_fd1d_handle* h, Fd1dBatch B, cudaStream_t st)
             return KW_FD1D_OK;
         }
         KW_CUDA(h, cudaEventRecord(h->ev0, st));
-        v->fn<<<grid, v->P, v->smem, st>>>(B);
+        v->fn<<<grid, v->pdes_per_cta > 1 ? 128 : v->P, v->smem, st>>>(B);
         h->launches += 1;
         KW_CUDA(h, cudaEventRecord(h->ev1, st));
         h->ev_valid = true;
@@ -559,14 +559,15 @@ int prepare_variant(kw_fd1d_handle* h, const RegVariant* var, const cudaDevicePr
     KW_CUDA(h, cudaFuncGetAttributes(&fa, var->fn));
     regs = fa.numRegs;
     int occ = 0;
-    KW_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, var->fn, var->P, var->smem));
+    const int block = var->pdes_per_cta > 1 ? 128 : var->P;  // Layout W: four warps = four PDEs
+    KW_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, var->fn, block, var->smem));
     if (occ < 1) return fail(h, KW_FD1D_ECUDA, "Fd1dGpu_Pricer::init: kernel variant does not fit on an SM");
     if (var->tmem_cols > 0) {
         // The occupancy calculator answers 1 for any kernel that allocates tensor memory, but the
         // hardware co-schedules CTAs as long as their tcgen05.alloc requests fit the SM's 512 columns
         // (measured: kw_fd1d_tmem_probe finds 4 x 128 columns resident).  Size the persistent grid
         // from the real limits: registers, shared memory, TMEM columns.
-        const int by_regs = 65536 / (fa.numRegs * var->P);
+        const int by_regs = 65536 / (fa.numRegs * block);
         const int by_smem = (int)((size_t)prop.sharedMemPerMultiprocessor / (var->smem + 1024));
         const int by_tmem = 512 / var->tmem_cols;
         occ = std::max(1, std::min({by_regs, by_smem, by_tmem, var->minb}));
