@@ -252,6 +252,29 @@ def test_edges_and_errors(oracle):
     assert kwfd1d.PricerFactory.create(cfg)[0].startswith("PricerFactory: Fd1dGpu_Pricer::init")
 
 
+@pytest.mark.parametrize("x,t,n,variants", [(1024, 48, 1500, (233,)), (2048, 32, 800, (331,)), (4096, 24, 400, (431,))])
+def test_range_error_in_warp_layouts(x, t, n, variants, oracle):
+    """The reference's out-of-range error (src/Math/kwFd1d.cpp:151-153) through the warp-per-PDE kernels:
+    batches big enough for the auto dispatch to take Layout W / wide Layout W, one bad option in the middle."""
+    from kwfd1d.synthetic import synthetic_options
+
+    o = synthetic_options(n, 77 + x)
+    o["k"][n // 2] = 1e-9  # log(s/k) far right of every grid
+    p = make_pricer(t, x)
+    err, got = p.price(o)
+    assert p.info()["variant"] in variants, p.info()["variant"]
+    assert err.startswith("Fd1d_Pricer::price Fd1d::value: x=") and "not in range" in err
+    assert np.isnan(got[n // 2]) and np.isfinite(np.delete(got, n // 2)).all()
+    good = np.delete(np.arange(n), n // 2)[:: max(1, n // 64)]
+    want, oerr = oracle.fd1d(o[good], t, x)
+    bar = TOL if t * 8 >= x else 5e-9
+    assert oerr == "" and maxdiff(got[good], want) <= bar
+    # the handle recovers
+    o["k"][n // 2] = 100.
+    err, got = p.price(o)
+    assert err == "" and np.isfinite(got).all()
+
+
 def test_smallest_grids(oracle):
     from kwfd1d.synthetic import synthetic_options
 
