@@ -325,7 +325,8 @@ __global__ void __launch_bounds__(128, MINB) fd1d_wide_kernel(const Fd1dBatch B,
                     group_barrier<32 * NWP>(grp);
                     double X = 0.;
 #pragma unroll
-                    for (int w = 0; w < 4; ++w) X = fma(lds_f64(a_cf + w * 8), lds_f64(a_zf + par + w * 8), X);
+                    for (int w = 0; w < NWP; ++w)  // the PDE's own slots only: another PDE's value times 0 may be NaN
+                        X = fma(lds_f64(a_cf + (w0 + w) * 8), lds_f64(a_zf + par + (w0 + w) * 8), X);
                     double Yin[NCH];
                     Yin[0] = fma(K(22), X, Sm1);
 #pragma unroll
@@ -347,7 +348,8 @@ __global__ void __launch_bounds__(128, MINB) fd1d_wide_kernel(const Fd1dBatch B,
                     group_barrier<32 * NWP>(grp);
                     double Xb = 0.;
 #pragma unroll
-                    for (int w = 0; w < 4; ++w) Xb = fma(lds_f64(a_cb + w * 8), lds_f64(a_zb + par + w * 8), Xb);
+                    for (int w = 0; w < NWP; ++w)
+                        Xb = fma(lds_f64(a_cb + (w0 + w) * 8), lds_f64(a_zb + par + (w0 + w) * 8), Xb);
                     double Uin[NCH];
                     Uin[NCH - 1] = fma(K(23), Xb, Tp1);
 #pragma unroll
