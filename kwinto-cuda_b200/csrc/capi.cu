@@ -69,6 +69,11 @@ struct RegVariant {
         ID, KW_FD1D_F64, 8, 128, MINB_, false, false, fd1d_warp_kernel<4, MINB_, ICMP_, PAIR_>,    \
             WarpSmem<4>::bytes(), 256, 4                                                           \
     }
+#define KW_VARIANT_WN(ID, NCH_, MINB_)                                                            \
+    {                                                                                              \
+        ID, KW_FD1D_F64, 8, 32 * NCH_, MINB_, false, false, fd1d_warp_kernel<NCH_, MINB_, false, true>, \
+            WarpSmem<NCH_>::bytes(), 64 * NCH_, 4                                                  \
+    }
 #define KW_VARIANT_W2(ID, MINB_, ICMP_)                                                           \
     {                                                                                              \
         ID, KW_FD1D_F64, 8, 128, MINB_, false, false, fd1d_warp2_kernel<4, MINB_, ICMP_>,          \
@@ -90,7 +95,8 @@ struct RegVariant {
 const RegVariant g_variants[] = {
     KW_VARIANT(1, 8, 32, 12, false, false),    // x <= 256
     KW_VARIANT(2, 8, 32, 16, true, true),
-    KW_VARIANT(101, 8, 64, 6, false, false),   // x <= 512
+    KW_VARIANT_WN(133, 2, 2),                  // x <= 512: Layout W with 2 chunks per lane (one chunk pair)
+    KW_VARIANT(101, 8, 64, 6, false, false),   // x <= 512, CTA per PDE (batches below one wave of Layout W)
     KW_VARIANT(102, 8, 64, 8, true, true),
     KW_VARIANT(103, 8, 64, 6, true, false),
     KW_VARIANT_W(233, 2, false, true),              // x <= 1024: Layout W (warp per PDE, coefficients in tensor memory), chunk pairs

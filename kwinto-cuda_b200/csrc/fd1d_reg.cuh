@@ -172,14 +172,15 @@ __device__ __forceinline__ float max_like_icmp(float a, float b)
 // threads, thread k owns the M nodes of chunk k.  Fills the x grid (xs, shared), the payoff v, the
 // projection floor pj (no_floor where the reference does not project) and the pivot-scaled LU of
 // B = 1 - dt/2 A:  a~ (a[0] = chunk-entry multiplier), g~ (g[M-1] = chunk-exit), D = 2/beta.
-// `scr` is >= 8*P doubles of shared scratch.  Contains __syncthreads(): call from every thread.
+// `scr` is >= 8*P doubles of shared scratch.  Contains __syncthreads(): call from every thread of the CTA
+// (groups of P threads work on different PDEs with their own xs / scr).
 template <int M, int P>
 __device__ __forceinline__ void setup_lu(const Fd1dBatch& B, const PdeScalars& sc, double no_floor, double* xs,
                                          double* scr, double (&v)[M], double (&pj)[M], double (&a)[M],
                                          double (&g)[M], double (&D)[M])
 {
     constexpr int N = M * P;
-    const int k = threadIdx.x;
+    const int k = threadIdx.x % P;  // a CTA wider than P sets several PDEs up side by side (own xs / scr each)
     const int lane = k & 31;
     const int warp = k >> 5;
     const int xDim = B.xDim;

@@ -43,9 +43,13 @@ template <int NCH>
 struct WarpSmem {
     static constexpr int N = 8 * NCH * 32;  // nodes per PDE tile
     static constexpr int P = 32 * NCH;      // set-up threads per PDE
-    // doubles: xs[4][N] | stage a, g, D, p, v [5][N] | chunk scalars A, G, R0 [3][P] | scratch [8*P] | misc [16]
-    //          | per-warp scan constants [4][22][32]
-    static constexpr size_t bytes() { return sizeof(double) * (size_t)(4 * N + 5 * N + 3 * P + 8 * P + 16 + 4 * 22 * 32); }
+    static constexpr int G = 128 / P;       // PDEs set up side by side
+    // doubles: xs[4][N] | stage a, g, D, p, v [G][5][N] | chunk scalars A, G, R0 [G][3][P] | scratch [G][8*P]
+    //          | misc [16] | per-warp scan constants [4][22][32]
+    static constexpr size_t bytes()
+    {
+        return sizeof(double) * (size_t)(4 * N + G * 5 * N + G * 3 * P + G * 8 * P + 16 + 4 * 22 * 32);
+    }
 };
 
 // PAIR: the chunk phase processes two chunks in lock step (two interleaved dependent chains per warp)
@@ -53,28 +57,33 @@ struct WarpSmem {
 template <int NCH, int MINB, bool ICMP, bool PAIR = false>
 __global__ void __launch_bounds__(128, MINB) fd1d_warp_kernel(const Fd1dBatch B)
 {
-    static_assert(NCH == 4, "set-up is shared with Layout B's 128-thread code: 4 chunks per lane (512 < x <= 1024)");
+    static_assert(NCH == 4 || (NCH == 2 && PAIR), "4 chunks per lane (512 < x <= 1024) or 2 (256 < x <= 512)");
     using L = WarpSmem<NCH>;
     constexpr int N = L::N;
-    constexpr int P = L::P;
+    constexpr int P = L::P;   // set-up threads per PDE (Layout B's cooperative set-up)
+    constexpr int G = L::G;   // PDEs set up side by side by the CTA's 128 threads
     constexpr int M = 8;
     constexpr int NODES = 8 * NCH;  // per lane
 
     extern __shared__ double smem[];
     double* xs = smem;                // [4][N]
-    double* st = xs + 4 * N;          // [5][N]: a, g, D, p, v of the PDE being set up; later the final v per warp
-    double* st_A = st + 5 * N;        // [P] chunk products of a~
-    double* st_G = st_A + P;          // [P] chunk products of g~
-    double* st_R0 = st_G + P;         // [P] response of a chunk's first backward value to its Yin
-    double* scr = st_R0 + P;          // [8 * P]
-    double* misc = scr + 8 * P;       // [16] spare
+    double* st_all = xs + 4 * N;          // [G][5][N]: a, g, D, p, v of the PDEs being set up; later the final v
+    double* stA_all = st_all + G * 5 * N; // [G][3][P]: chunk products of a~, of g~, response R0
+    double* scr_all = stA_all + G * 3 * P;  // [G][8 * P]
+    double* misc = scr_all + G * 8 * P;   // [16] spare
     double* wconst = misc + 16;       // [4 warps][22][32 lanes] scan constants of the warp's PDE
 
-    const int k = threadIdx.x;
-    const int lane = k & 31;
-    const int warp = k >> 5;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int sg = threadIdx.x / P;   // set-up group of this thread
+    const int k = threadIdx.x % P;    // its chunk in the group's PDE
     const int xDim = B.xDim;
     const int nsteps = B.tDim - 1;
+    double* st = st_all + sg * (5 * N);
+    double* st_A = stA_all + sg * (3 * P);
+    double* st_G = st_A + P;
+    double* st_R0 = st_G + P;
+    double* scr = scr_all + sg * (8 * P);
 
     // tensor memory: 4 arrays x 8*NCH doubles per lane = 64*NCH columns per warp
     __shared__ uint32_t s_taddr;
@@ -93,10 +102,12 @@ __global__ void __launch_bounds__(128, MINB) fd1d_warp_kernel(const Fd1dBatch B)
         double bmax_mine = 1.;
         bool put_mine = true;
 
-        // ---------------- set-up, one PDE at a time, all 128 threads ---------------------------
-        for (int q = 0; q < 4; ++q) {
-            const uint32_t pde = 4 * grp + q;
-            if (pde >= n_pde) break;  // uniform across the CTA
+        // ---------------- set-up: G PDEs at a time, P threads each --------------------------------
+        for (int q0 = 0; q0 < 4; q0 += G) {
+            if (4 * grp + q0 >= n_pde) break;  // uniform across the CTA
+            const int q = q0 + sg;
+            const bool q_valid = 4 * grp + q < n_pde;
+            const uint32_t pde = q_valid ? 4 * grp + q : n_pde - 1;  // a missing PDE is set up as a copy (barriers stay uniform)
             const uint32_t rep = B.pde_rep ? __ldg(B.pde_rep + pde) : pde;
             const kw_option opt = load_option(B.opts + rep);
             const PdeScalars sc = pde_scalars(opt, B);
@@ -120,7 +131,7 @@ __global__ void __launch_bounds__(128, MINB) fd1d_warp_kernel(const Fd1dBatch B)
 #pragma unroll
                 for (int d = 16; d >= 1; d >>= 1) bmax = fmax(bmax, __shfl_xor_sync(FULL, bmax, d));
                 __syncthreads();  // setup_lu's scratch is free
-                if (lane == 0) scr[warp] = bmax;
+                if (lane == 0) scr[k >> 5] = bmax;
 #pragma unroll
                 for (int i = 0; i < M; ++i) {
                     st[0 * N + k * M + i] = a[i];
@@ -134,8 +145,14 @@ __global__ void __launch_bounds__(128, MINB) fd1d_warp_kernel(const Fd1dBatch B)
                 st_R0[k] = R0;
             }
             __syncthreads();
-            if (warp == q) {
-                // the owner pulls its lane's NCH chunks: coefficient arrays into TMEM, v into registers
+            if (warp >= q0 && warp < q0 + G && 4 * grp + warp < n_pde) {
+                // the owner pulls its lane's NCH chunks: coefficient arrays into TMEM, v into registers;
+                // warp q0 + j owns the PDE that set-up group j just prepared
+                const double* st = st_all + (warp - q0) * (5 * N);
+                const double* st_A = stA_all + (warp - q0) * (3 * P);
+                const double* st_G = st_A + P;
+                const double* st_R0 = st_G + P;
+                const double* scr = scr_all + (warp - q0) * (8 * P);
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) {
                     const int ch = lane * NCH + c;
@@ -155,9 +172,11 @@ __global__ void __launch_bounds__(128, MINB) fd1d_warp_kernel(const Fd1dBatch B)
                 tmem::wait_st();
                 double bm = scr[0];
 #pragma unroll
-                for (int w = 1; w < 4; ++w) bm = fmax(bm, scr[w]);
+                for (int w = 1; w < P / 32; ++w) bm = fmax(bm, scr[w]);
                 bmax_mine = bm;
-                put_mine = sc.put;
+                // the owner's PDE may differ from the one this thread helped to set up: read its flag directly
+                const uint32_t rep_own = B.pde_rep ? __ldg(B.pde_rep + 4 * grp + warp) : 4 * grp + warp;
+                put_mine = load_option(B.opts + rep_own).w < 0;
             }
             __syncthreads();
         }
@@ -397,7 +416,7 @@ __global__ void __launch_bounds__(128, MINB) fd1d_warp_kernel(const Fd1dBatch B)
                 atomicAdd(&B.status[2 + bucket], 1u);
             }
             // ---------------- epilogue: interpolate every option of this chain -------------------
-            double* vfin = st + warp * N;  // the stage is free: set-up finished before the march
+            double* vfin = st_all + warp * N;  // the stage is free: set-up finished before the march
 #pragma unroll
             for (int i = 0; i < NODES; ++i) vfin[lane * NODES + i] = vr[i];
             __syncwarp();

@@ -100,7 +100,7 @@ def test_all_1024_variants(variant):
     assert err == "" and maxdiff(got, g["mix_1024/fd1d"]) <= TOL
 
 
-@pytest.mark.parametrize("variant,x", [(1, 256), (2, 256), (101, 512), (102, 512), (103, 512), (301, 2048),
+@pytest.mark.parametrize("variant,x", [(1, 256), (2, 256), (101, 512), (102, 512), (103, 512), (133, 512), (133, 300), (301, 2048),
                                         (302, 2048), (401, 4096), (402, 4096), (331, 2048), (331, 1100), (431, 4096), (431, 3000)])
 def test_other_variants(variant, x, oracle):
     from kwfd1d.synthetic import synthetic_options
@@ -120,14 +120,15 @@ def test_device_side_compression_matches_host_side():
     bit for bit, and the same number of PDEs as the reference finds (600 chains in the fixture)."""
     g = load_golden("portfolio_fd1d")
     o = g["options"]
-    res = {}
-    for c in (0, 1, 2):
-        p = make_pricer(128, 512, **{"FD1D.GPU.COMPRESS": c})
-        err, got = p.price(o)
-        assert err == ""
-        res[c] = got
-        assert p.info()["last_n_pde"] == (6000 if c == 0 else 600), (c, p.info()["last_n_pde"])
-    assert np.array_equal(res[0], res[1]) and np.array_equal(res[1], res[2])
+    for variant in (101, 133):  # the kernel is pinned: the auto dispatch picks it from the PDE count
+        res = {}
+        for c in (0, 1, 2):
+            p = make_pricer(128, 512, **{"FD1D.GPU.COMPRESS": c, "FD1D.GPU.VARIANT": variant})
+            err, got = p.price(o)
+            assert err == ""
+            res[c] = got
+            assert p.info()["last_n_pde"] == (6000 if c == 0 else 600), (c, p.info()["last_n_pde"])
+        assert np.array_equal(res[0], res[1]) and np.array_equal(res[1], res[2]), variant
     # many members per chain, more chains than resident CTAs, a NaN key and a -0.0 key in the batch
     rng = np.random.default_rng(5)
     base = g["options"][::10][:600].copy()
@@ -190,8 +191,8 @@ def test_wide_layout_w(x, t, n, oracle):
 def test_compression_and_permutation_are_bit_neutral():
     g = load_golden("portfolio_fd1d")
     o = g["options"]
-    a = make_pricer(256, 512)
-    b = make_pricer(256, 512, **{"FD1D.GPU.COMPRESS": 0})
+    a = make_pricer(256, 512, **{"FD1D.GPU.VARIANT": 133})  # same kernel on both sides (auto picks by PDE count)
+    b = make_pricer(256, 512, **{"FD1D.GPU.COMPRESS": 0, "FD1D.GPU.VARIANT": 133})
     _, pa = a.price(o)
     _, pb = b.price(o[:1500])
     assert a.info()["last_n_pde"] == 600 and b.info()["last_n_pde"] == 1500
