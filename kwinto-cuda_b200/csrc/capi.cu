@@ -19,6 +19,7 @@
 #include "fd1d_soa.cuh"
 #include "fd1d_warp.cuh"
 #include "fd1d_wide.cuh"
+#include "fd1d_warpf.cuh"
 #include "compress.cuh"
 #include "microbench.cuh"
 
@@ -74,6 +75,11 @@ struct RegVariant {
         ID, KW_FD1D_F64, 8, 32 * NCH_, MINB_, false, false, fd1d_warp_kernel<NCH_, MINB_, false, true>, \
             WarpSmem<NCH_>::bytes(), 64 * NCH_, 4                                                  \
     }
+#define KW_VARIANT_WF(ID, NCH_, MINB_)                                                            \
+    {                                                                                              \
+        ID, KW_FD1D_F32, 8, 32 * NCH_, MINB_, false, false, fd1d_warpf_kernel<NCH_, MINB_, false, true, float>, \
+            WarpSmem<NCH_>::bytes(), 32 * NCH_, 4                                                  \
+    }
 #define KW_VARIANT_W2(ID, MINB_, ICMP_)                                                           \
     {                                                                                              \
         ID, KW_FD1D_F64, 8, 128, MINB_, false, false, fd1d_warp2_kernel<4, MINB_, ICMP_>,          \
@@ -123,6 +129,8 @@ const RegVariant g_variants[] = {
     // fp32 march (fp64 set-up): FD1D.GPU.PRECISION = f32
     KW_VARIANT_F32(1001, 8, 32, 16),
     KW_VARIANT_F32(1101, 8, 64, 8),
+    KW_VARIANT_WF(1133, 2, 2),   // Layout W, float march, 256 < x <= 512 (slower than 1101: 6.0 M vs 7.1 M options/s)
+    KW_VARIANT_WF(1233, 4, 2),   // Layout W, float march, 512 < x <= 1024
     KW_VARIANT_F32(1201, 8, 128, 4),
     KW_VARIANT_F32(1301, 8, 256, 2),
     KW_VARIANT_F32(1401, 8, 512, 1),

@@ -121,6 +121,30 @@ __device__ __forceinline__ uint32_t ld16_raw(uint32_t taddr)
         : "memory");
     return r[0] ^ r[5] ^ r[10] ^ r[15];
 }
+// the same for eight floats (eight columns)
+__device__ __forceinline__ void ld8(uint32_t taddr, float (&d)[8])
+{
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void st8(uint32_t taddr, const float (&d)[8])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};" ::"r"(__float_as_uint(d[0])),
+                 "r"(__float_as_uint(d[1])), "r"(__float_as_uint(d[2])), "r"(__float_as_uint(d[3])),
+                 "r"(__float_as_uint(d[4])), "r"(__float_as_uint(d[5])), "r"(__float_as_uint(d[6])),
+                 "r"(__float_as_uint(d[7])), "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void wait_ld_dep(float (&d)[8])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]), "+f"(d[4]), "+f"(d[5]), "+f"(d[6]), "+f"(d[7])::"memory");
+}
 // the wait, tied to the loaded values so that the compiler cannot consume them earlier
 __device__ __forceinline__ void wait_ld_dep(double (&d)[8])
 {

@@ -405,6 +405,22 @@ def test_fp32_march_fixtures(grid):
         assert rel <= 1e-4 and ab <= 5e-5, (name, grid, rel, ab)
 
 
+@pytest.mark.parametrize("x,t,n,variant", [(1024, 200, 1500, 1233), (512, 300, 1500, 1133), (700, 128, 1300, 1233)])
+def test_fp32_march_layout_w(x, t, n, variant, oracle):
+    """The fp32 march in Layout W (fd1d_warpf.cuh): batches of a device wave or more."""
+    from kwfd1d.synthetic import synthetic_options
+
+    o = synthetic_options(n, 2000 + x, european_every=5, call_every=3)
+    want, oerr = oracle.fd1d(o, t, x)
+    p = make_pricer(t, x, **{"FD1D.GPU.PRECISION": "f32", "FD1D.GPU.VARIANT": variant})
+    err, got = p.price(o)
+    assert err == oerr == ""
+    assert p.info()["variant"] == variant, p.info()["variant"]
+    rel, ab = fp32_error(got, want)
+    print("fp32 layout W", x, t, n, "rel", rel, "abs", ab, p.info()["mode_count"])
+    assert rel <= 1e-4 and ab <= 5e-5, (x, t, rel, ab)
+
+
 def test_fp32_march_synthetic_shapes(oracle):
     from kwfd1d.synthetic import synthetic_options
 
