@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -20,6 +21,7 @@
 #include "fd1d_warp.cuh"
 #include "fd1d_wide.cuh"
 #include "fd1d_warpf.cuh"
+#include "fd1d_warp_bs.cuh"
 #include "compress.cuh"
 #include "microbench.cuh"
 
@@ -135,6 +137,10 @@ const RegVariant g_variants[] = {
     KW_VARIANT_F32(1301, 8, 256, 2),
     KW_VARIANT_F32(1401, 8, 512, 1),
 };
+constexpr int kDefaultSkewPermille = 0;
+// fused FD1D-BS march (fd1d_warp_bs.cuh): the solution as given and its European copy in one warp
+const RegVariant g_bs_variant = {251, KW_FD1D_F64, 8, 128, 2, false, false, fd1d_warp_bs_kernel<2>,
+                                 Warp2Smem<4>::bytes(), 256, 4};
 constexpr int kNumVariants = sizeof(g_variants) / sizeof(g_variants[0]);
 constexpr int kMaxRegX = 4096;
 
@@ -278,6 +284,10 @@ struct kw_fd1d_handle {
     int ctas_per_sm_small = 0;
     int regs_small = 0;
     uint32_t small_below = 0;
+    int skew_permille = 0;                  // Layout W start-up skew in thousandths of a group period (0 = none)
+    const RegVariant* var_bs = nullptr;     // fused FD1D-BS march, when the configuration has one
+    int ctas_per_sm_bs = 0;
+    int regs_bs = 0;
     const RegVariant* last_var = nullptr;   // what the last batch ran
     int last_grid = 0;
     int launches = 0;  // kernels launched by the current / last price call
@@ -333,10 +343,12 @@ int launch_batch(kw_fd1d_handle* h, Fd1dBatch B, cudaStream_t st)
     h->launches += 1;
     h->last_n_pde = B.n_pde;
     if (h->layout == KW_FD1D_LAYOUT_REG) {
-        const bool small = h->var_small && B.n_pde < h->small_below;
-        const RegVariant* v = small ? h->var_small : h->var;
+        const bool fused = B.prices_eu != nullptr;
+        if (fused && !h->var_bs) return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::price: no fused FD1D-BS kernel for this configuration");
+        const bool small = !fused && h->var_small && B.n_pde < h->small_below;
+        const RegVariant* v = fused ? h->var_bs : (small ? h->var_small : h->var);
         h->last_var = v;
-        int grid = h->sm_count * (small ? h->ctas_per_sm_small : h->ctas_per_sm);
+        int grid = h->sm_count * (fused ? h->ctas_per_sm_bs : (small ? h->ctas_per_sm_small : h->ctas_per_sm));
         const uint32_t ppc = v->pdes_per_cta > 1 ? (uint32_t)v->pdes_per_cta : 1u;
         const uint32_t want = (B.n_pde + ppc - 1) / ppc;  // with device-side compression n_pde = n is an upper bound
         if ((uint32_t)grid > want) grid = (int)want;
@@ -365,6 +377,13 @@ int launch_batch(kw_fd1d_handle* h, Fd1dBatch B, cudaStream_t st)
             h->ev_valid = true;
             KW_CUDA(h, cudaGetLastError());
             return KW_FD1D_OK;
+        }
+        if (v->pdes_per_cta > 1 && h->skew_permille > 0 && want >= 4u * (uint32_t)grid && (grid & 1) == 0) {
+            // Layout W, several rounds of a full persistent grid: start the grid's second half about half a
+            // group period late (fd1d_common.cuh: skew_start).  Period model: time steps x the measured
+            // per-step time of the kernel family with two CTAs per SM.
+            const double ns_per_step = v->id == 251 ? 1900. : (v->prec == KW_FD1D_F32 ? 0.56 : 1.) * (v->P == 64 ? 520. : 1040.);
+            B.skew_ns = (uint32_t)std::min(4e8, 1e-3 * h->skew_permille * ns_per_step * (double)(B.tDim - 1));
         }
         KW_CUDA(h, cudaEventRecord(h->ev0, st));
         v->fn<<<grid, v->pdes_per_cta > 1 ? 128 : v->P, v->smem, st>>>(B);
@@ -490,7 +509,7 @@ int compress_on_device(kw_fd1d_handle* h, Fd1dBatch& B, const kw_option* d_opts,
 
 // host assets -> device prices in `d_out` (n doubles) on the handle's stream; no final sync
 int price_to_device(kw_fd1d_handle* h, const kw_option* assets, size_t n, DevBuf<kw_option>& d_opts,
-                    double* d_out)
+                    double* d_out, double* d_out_eu = nullptr)
 {
     KW_CUDA(h, d_opts.reserve(n));
     KW_CUDA(h, h->d_status.reserve(8));
@@ -499,6 +518,7 @@ int price_to_device(kw_fd1d_handle* h, const kw_option* assets, size_t n, DevBuf
     memset(&B, 0, sizeof B);
     B.opts = d_opts.p;
     B.prices = d_out;
+    B.prices_eu = d_out_eu;  // non-null: the fused FD1D-BS march (both solutions of every chain)
     B.status = h->d_status.p;
     B.tDim = (int32_t)h->cfg.t_grid_size;
     B.xDim = (int32_t)h->cfg.x_grid_size;
@@ -636,6 +656,8 @@ int kw_fd1d_create(const kw_fd1d_config* cfg, kw_fd1d_handle** out)
         return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::init: FD1D.T_GRID_SIZE must be >= 2 and FD1D.X_GRID_SIZE >= 3");
     if (!(cfg->density > 0) || !(cfg->scale > 0))
         return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::init: FD1D.DENSITY and FD1D.SCALE must be positive");
+    if (cfg->bs_fused < 0 || cfg->bs_fused > 2)
+        return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::init: FD1D.GPU.BS_FUSED must be 0, 1 or 2");
     if (cfg->exact < 0 || cfg->exact > 2)
         return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::init: FD1D.GPU.EXACT must be 0, 1 or 2");
     if (cfg->precision != KW_FD1D_F64 && cfg->precision != KW_FD1D_F32)
@@ -675,6 +697,12 @@ int kw_fd1d_create(const kw_fd1d_config* cfg, kw_fd1d_handle** out)
                 h->small_below = (uint32_t)(h->sm_count * h->ctas_per_sm * std::max(1, h->var->pdes_per_cta));
             }
         }
+        // fused FD1D-BS march: fp64, one Layout W tile of 4 chunks per lane
+        if (cfg->bs_fused != 1 && cfg->precision == KW_FD1D_F64 && cfg->x_grid_size > 512 && cfg->x_grid_size <= 1024 &&
+            (cfg->variant == 0 || cfg->bs_fused == 2)) {
+            h->var_bs = &g_bs_variant;
+            if (int rc = prepare_variant(h, h->var_bs, prop, h->ctas_per_sm_bs, h->regs_bs)) return rc;
+        }
     } else if (layout == KW_FD1D_LAYOUT_SOA) {
         if (cfg->precision != KW_FD1D_F64)
             return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::init: the SoA layout (FD1D.GPU.LAYOUT = soa) is fp64 only");
@@ -686,6 +714,8 @@ int kw_fd1d_create(const kw_fd1d_config* cfg, kw_fd1d_handle** out)
         return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::init: unknown FD1D.GPU.LAYOUT");
     }
     h->layout = layout;
+    h->skew_permille = kDefaultSkewPermille;
+    if (const char* e = getenv("KW_FD1D_SKEW_PERMILLE")) h->skew_permille = std::max(0, std::min(1000, atoi(e)));  // tuning knob
     KW_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     KW_CUDA(h, cudaEventCreate(&h->ev0));
     KW_CUDA(h, cudaEventCreate(&h->ev1));
@@ -747,6 +777,16 @@ int kw_fd1d_price_bs(kw_fd1d_handle* h, const kw_option* assets, size_t n, doubl
     KW_CUDA(h, cudaSetDevice(h->cfg.device));
     KW_CUDA(h, h->d_prices.reserve(n));
     KW_CUDA(h, h->d_prices2.reserve(n));
+    if (h->var_bs && (h->cfg.bs_fused == 2 || n >= (size_t)h->sm_count * h->ctas_per_sm_bs * 4)) {
+        // fused: the solve as given (:18) and the solve of the European copies (:21-28) are two value
+        // vectors of the same chains marched by one launch; then + (BS - FD_euro) (:30-40)
+        if (int rc = price_to_device(h, assets, n, h->d_opts, h->d_prices.p, h->d_prices2.p)) return rc;
+        bs_combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_opts.p, n, h->d_prices.p, h->d_prices2.p);
+        h->launches += 1;
+        KW_CUDA(h, cudaGetLastError());
+        KW_CUDA(h, cudaMemcpyAsync(prices, h->d_prices.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        return check_status(h, h->stream, assets);
+    }
     // 1. FD as given (src/Pricer/kwFd1d_BlackScholes.cpp:18)
     if (int rc = price_to_device(h, assets, n, h->d_opts, h->d_prices.p)) return rc;
     if (int rc = check_status(h, h->stream, assets)) return rc;
@@ -837,8 +877,9 @@ int kw_fd1d_get_info(const kw_fd1d_handle* hc, kw_fd1d_info* info)
     const bool lw = lv && (lv->pdes_per_cta > 1 || lv->wide_nwp);  // Layout W: 32 nodes per lane
     info->threads_per_pde = lv ? (lv->wide_nwp ? 32 * lv->wide_nwp : (lw ? 32 : lv->P)) : 1;
     info->nodes_per_thread = lv ? (lw ? 32 : lv->M) : (int)h->cfg.x_grid_size;
-    info->ctas_per_sm = lsmall ? h->ctas_per_sm_small : h->ctas_per_sm;
-    info->regs_per_thread = lsmall ? h->regs_small : h->regs;
+    const bool lbs = lv && lv == h->var_bs;
+    info->ctas_per_sm = lbs ? h->ctas_per_sm_bs : (lsmall ? h->ctas_per_sm_small : h->ctas_per_sm);
+    info->regs_per_thread = lbs ? h->regs_bs : (lsmall ? h->regs_small : h->regs);
     info->smem_per_cta = lv ? (int)lv->smem : 0;
     info->grid = h->last_grid;
     info->sm_clock_khz = h->clock_khz;

@@ -39,6 +39,7 @@ public:
         c.compress = (int32_t)config.get("FD1D.GPU.COMPRESS", 1);
         c.variant = (int32_t)config.get("FD1D.GPU.VARIANT", 0);
         c.exact = (int32_t)config.get("FD1D.GPU.EXACT", 0);
+        c.bs_fused = (int32_t)config.get("FD1D.GPU.BS_FUSED", 0);
         const std::string layout = config.get("FD1D.GPU.LAYOUT", "auto");
         if (layout == "auto")
             c.layout = KW_FD1D_LAYOUT_AUTO;

@@ -35,7 +35,7 @@ class _CConfig(C.Structure):  # struct kw_fd1d_config
     _fields_ = [("density", C.c_double), ("scale", C.c_double), ("t_grid_size", C.c_int64),
                 ("x_grid_size", C.c_int64), ("device", C.c_int32), ("precision", C.c_int32),
                 ("layout", C.c_int32), ("compress", C.c_int32), ("variant", C.c_int32),
-                ("exact", C.c_int32), ("reserved", C.c_int32 * 2)]
+                ("exact", C.c_int32), ("bs_fused", C.c_int32), ("reserved", C.c_int32)]
 
 
 class _CInfo(C.Structure):  # struct kw_fd1d_info
@@ -150,7 +150,8 @@ class Fd1dGpu_Pricer(Pricer):
     reference (src/Pricer/kwFd1d.cpp:12-16) plus FD1D.GPU.DEVICE (int), FD1D.GPU.LAYOUT
     ("auto"|"reg"|"soa"), FD1D.GPU.PRECISION ("f64"), FD1D.GPU.COMPRESS (int 0/1),
     FD1D.GPU.VARIANT (int), FD1D.GPU.EXACT (int 0/1/2: 0 lets provably negligible carry terms be
-    dropped, 2 keeps every term)."""
+    dropped, 2 keeps every term), FD1D.GPU.BS_FUSED (int 0/1/2, "FD1D-BS-GPU" only: 0 = the fused
+    American + European march where it applies, 1 = two separate solves, 2 = fused for every batch size)."""
 
     _mode_bs = False
 
@@ -179,6 +180,7 @@ class Fd1dGpu_Pricer(Pricer):
         c.compress = config.get("FD1D.GPU.COMPRESS", 1)
         c.variant = config.get("FD1D.GPU.VARIANT", 0)
         c.exact = config.get("FD1D.GPU.EXACT", 0)
+        c.bs_fused = config.get("FD1D.GPU.BS_FUSED", 0)
         h = C.c_void_p()
         rc = self._lib.kw_fd1d_create(C.byref(c), C.byref(h))
         if rc != KW_FD1D_OK:

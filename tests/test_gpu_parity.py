@@ -79,6 +79,59 @@ def test_synthetic_golden_all_shapes():
     assert err == "" and maxdiff(got, g["bs_mix/fd1d_bs"]) <= TOL
 
 
+@pytest.mark.parametrize("key", ["bs_1024", "bs_700x200", "bs_513x64"])
+def test_fd1d_bs_fused_march(key):
+    # src/Pricer/kwFd1d_BlackScholes.cpp:15-43 with both solves of a chain marched by one launch
+    # (fd1d_warp_bs.cuh, variant 251): against the reference's FD1D-BS prices and against the
+    # two-solve path of the same library
+    g = load_golden("bs_fused")
+    t, x = (int(v) for v in g[key + "/grid"])
+    o = g[key + "/options"]
+    fused = make_pricer(t, x, mode="FD1D-BS-GPU", **{"FD1D.GPU.BS_FUSED": 2})
+    err, got = fused.price(o)
+    assert err == "", err
+    info = fused.info()
+    assert info["variant"] == 251, info
+    n_chain = len({(r["t"], r["r"], r["q"], r["z"], r["e"], r["w"]) for r in o})
+    assert info["last_n_pde"] == n_chain
+    assert maxdiff(got, g[key + "/fd1d_bs"]) <= TOL, maxdiff(got, g[key + "/fd1d_bs"])
+    two = make_pricer(t, x, mode="FD1D-BS-GPU", **{"FD1D.GPU.BS_FUSED": 1})
+    err, got2 = two.price(o)
+    assert err == "" and two.info()["variant"] != 251
+    assert maxdiff(got2, g[key + "/fd1d_bs"]) <= TOL
+    assert maxdiff(got, got2) <= 1e-10
+    # the same handle still prices plain FD1D through kw_fd1d_price with the default kernel
+    plain = make_pricer(t, x)
+    err, gotp = plain.price(o)
+    assert err == "" and maxdiff(gotp, g[key + "/fd1d"]) <= TOL
+
+
+def test_fd1d_bs_fused_range_error_and_dispatch():
+    from kwfd1d.synthetic import synthetic_options
+
+    # an out-of-range option fails the fused call with the reference's message; the others are priced
+    g = load_golden("bs_fused")
+    o = g["bs_700x200/options"].copy()
+    want = g["bs_700x200/fd1d_bs"]
+    o["s"][3] = 1e9
+    p = make_pricer(200, 700, mode="FD1D-BS-GPU", **{"FD1D.GPU.BS_FUSED": 2})
+    err, got = p.price(o)
+    assert "not in range" in err and np.isnan(got[3])
+    keep = np.arange(o.shape[0]) != 3
+    assert maxdiff(got[keep], want[keep]) <= TOL
+    # auto dispatch: small batches take the two-solve path, a device wave or more the fused kernel
+    auto = make_pricer(64, 1024, mode="FD1D-BS-GPU")
+    err, small = auto.price(synthetic_options(64, 5))
+    assert err == "" and auto.info()["variant"] != 251
+    big = synthetic_options(2048, 5, european_every=7)
+    err, a = auto.price(big)
+    assert err == "" and auto.info()["variant"] == 251
+    two = make_pricer(64, 1024, mode="FD1D-BS-GPU", **{"FD1D.GPU.BS_FUSED": 1})
+    err, b = two.price(big)
+    assert err == "" and maxdiff(a, b) <= 1e-10
+    assert maxdiff(a[:64], small) <= 1e-10
+
+
 @pytest.mark.parametrize("layout", ["reg", "soa"])
 def test_layouts_agree_with_reference(layout):
     g, _ = synthetic_cases()
