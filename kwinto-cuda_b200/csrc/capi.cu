@@ -137,7 +137,6 @@ const RegVariant g_variants[] = {
     KW_VARIANT_F32(1301, 8, 256, 2),
     KW_VARIANT_F32(1401, 8, 512, 1),
 };
-constexpr int kDefaultSkewPermille = 0;
 // fused FD1D-BS march (fd1d_warp_bs.cuh): the solution as given and its European copy in one warp
 const RegVariant g_bs_variant = {251, KW_FD1D_F64, 8, 128, 2, false, false, fd1d_warp_bs_kernel<2>,
                                  Warp2Smem<4>::bytes(), 256, 4};
@@ -284,7 +283,6 @@ struct kw_fd1d_handle {
     int ctas_per_sm_small = 0;
     int regs_small = 0;
     uint32_t small_below = 0;
-    int skew_permille = 0;                  // Layout W start-up skew in thousandths of a group period (0 = none)
     const RegVariant* var_bs = nullptr;     // fused FD1D-BS march, when the configuration has one
     int ctas_per_sm_bs = 0;
     int regs_bs = 0;
@@ -377,13 +375,6 @@ int launch_batch(kw_fd1d_handle* h, Fd1dBatch B, cudaStream_t st)
             h->ev_valid = true;
             KW_CUDA(h, cudaGetLastError());
             return KW_FD1D_OK;
-        }
-        if (v->pdes_per_cta > 1 && h->skew_permille > 0 && want >= 4u * (uint32_t)grid && (grid & 1) == 0) {
-            // Layout W, several rounds of a full persistent grid: start the grid's second half about half a
-            // group period late (fd1d_common.cuh: skew_start).  Period model: time steps x the measured
-            // per-step time of the kernel family with two CTAs per SM.
-            const double ns_per_step = v->id == 251 ? 1900. : (v->prec == KW_FD1D_F32 ? 0.56 : 1.) * (v->P == 64 ? 520. : 1040.);
-            B.skew_ns = (uint32_t)std::min(4e8, 1e-3 * h->skew_permille * ns_per_step * (double)(B.tDim - 1));
         }
         KW_CUDA(h, cudaEventRecord(h->ev0, st));
         v->fn<<<grid, v->pdes_per_cta > 1 ? 128 : v->P, v->smem, st>>>(B);
@@ -657,7 +648,7 @@ int kw_fd1d_create(const kw_fd1d_config* cfg, kw_fd1d_handle** out)
     if (!(cfg->density > 0) || !(cfg->scale > 0))
         return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::init: FD1D.DENSITY and FD1D.SCALE must be positive");
     if (cfg->bs_fused < 0 || cfg->bs_fused > 2)
-        return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::init: FD1D.GPU.BS_FUSED must be 0, 1 or 2");
+        return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::init: FD1D.GPU.BS_FUSED must be 0 or 2");
     if (cfg->exact < 0 || cfg->exact > 2)
         return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::init: FD1D.GPU.EXACT must be 0, 1 or 2");
     if (cfg->precision != KW_FD1D_F64 && cfg->precision != KW_FD1D_F32)
@@ -698,8 +689,7 @@ int kw_fd1d_create(const kw_fd1d_config* cfg, kw_fd1d_handle** out)
             }
         }
         // fused FD1D-BS march: fp64, one Layout W tile of 4 chunks per lane
-        if (cfg->bs_fused != 1 && cfg->precision == KW_FD1D_F64 && cfg->x_grid_size > 512 && cfg->x_grid_size <= 1024 &&
-            (cfg->variant == 0 || cfg->bs_fused == 2)) {
+        if (cfg->bs_fused == 2 && cfg->precision == KW_FD1D_F64 && cfg->x_grid_size > 512 && cfg->x_grid_size <= 1024) {
             h->var_bs = &g_bs_variant;
             if (int rc = prepare_variant(h, h->var_bs, prop, h->ctas_per_sm_bs, h->regs_bs)) return rc;
         }
@@ -714,8 +704,6 @@ int kw_fd1d_create(const kw_fd1d_config* cfg, kw_fd1d_handle** out)
         return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::init: unknown FD1D.GPU.LAYOUT");
     }
     h->layout = layout;
-    h->skew_permille = kDefaultSkewPermille;
-    if (const char* e = getenv("KW_FD1D_SKEW_PERMILLE")) h->skew_permille = std::max(0, std::min(1000, atoi(e)));  // tuning knob
     KW_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     KW_CUDA(h, cudaEventCreate(&h->ev0));
     KW_CUDA(h, cudaEventCreate(&h->ev1));
@@ -777,7 +765,9 @@ int kw_fd1d_price_bs(kw_fd1d_handle* h, const kw_option* assets, size_t n, doubl
     KW_CUDA(h, cudaSetDevice(h->cfg.device));
     KW_CUDA(h, h->d_prices.reserve(n));
     KW_CUDA(h, h->d_prices2.reserve(n));
-    if (h->var_bs && (h->cfg.bs_fused == 2 || n >= (size_t)h->sm_count * h->ctas_per_sm_bs * 4)) {
+    if (h->cfg.bs_fused == 2 && !h->var_bs)
+        return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::price: FD1D.GPU.BS_FUSED = 2 needs fp64 and 512 < FD1D.X_GRID_SIZE <= 1024");
+    if (h->var_bs) {
         // fused: the solve as given (:18) and the solve of the European copies (:21-28) are two value
         // vectors of the same chains marched by one launch; then + (BS - FD_euro) (:30-40)
         if (int rc = price_to_device(h, assets, n, h->d_opts, h->d_prices.p, h->d_prices2.p)) return rc;

@@ -43,28 +43,7 @@ struct Fd1dBatch {
     double density;
     double scale;
     double* prices_eu;     // fused FD1D-BS march only (fd1d_warp_bs.cuh): the European solution's prices
-    uint32_t skew_ns;      // Layout W: the second half of the persistent grid starts this much later, so that the
-                           // two CTAs of an SM alternate set-up and march instead of setting up in lock step
 };
-
-// Start-up skew of a persistent Layout W grid.  All PDEs of a batch cost the same, so the two resident CTAs
-// of an SM would run their latency-bound set-up phases at the same moments for the whole launch; delaying
-// the CTAs of the grid's second half by about half a group period keeps one CTA marching (FP64 pipe busy)
-// while the other sets up.  Results do not depend on it.
-__device__ __forceinline__ void skew_start(const Fd1dBatch& B)
-{
-    if (B.skew_ns != 0u && 2 * blockIdx.x >= gridDim.x) {
-        if (threadIdx.x == 0) {
-            unsigned long long t0, t1;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-            do {
-                __nanosleep(1000);
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            } while (t1 - t0 < (unsigned long long)B.skew_ns);
-        }
-        __syncthreads();
-    }
-}
 
 __device__ __forceinline__ uint32_t batch_n_pde(const Fd1dBatch& B)
 {

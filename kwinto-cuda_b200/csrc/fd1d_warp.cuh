@@ -96,7 +96,6 @@ __global__ void __launch_bounds__(128, MINB) fd1d_warp_kernel(const Fd1dBatch B)
 
     const uint32_t n_pde = batch_n_pde(B);
     const uint32_t n_grp = (n_pde + 3) / 4;
-    skew_start(B);
     for (uint32_t grp = blockIdx.x; grp < n_grp; grp += gridDim.x) {
         double vr[NODES];              // this lane's nodes of PDE 4*grp + warp
         double Ac[NCH], Gc[NCH], R0c[NCH];

@@ -17,6 +17,13 @@
 // The epilogue interpolates both solutions for every option of the chain: prices[] (as given) and
 // prices_eu[] (European); the caller adds the closed form (bs_combine_kernel, capi.cu).
 // Set-up, truncation proof, launch geometry: fd1d_warp2_kernel's.  512 < xDim <= 1024.
+//
+// MEASURED (profiles/r1_as_*, r1_at_*): prices bit-identical to the two-solve path, but 82.6 ms against
+// 2 x 29.2 ms for 32768 chains at 1024^2.  The fully unrolled step is ~800 instructions (12.7 KB); ncu
+// reports stall_no_instruction = 3.8 cycles per issued instruction (0.06 for the 444-instruction step of
+// fd1d_warp_kernel): the loop no longer fits the instruction cache, and ptxas schedules only 30 of the 340
+// DFMAs next to their partner (.reuse).  Hence opt-in (FD1D.GPU.BS_FUSED = 2), not the default; a version
+// that fits needs a rolled chunk loop with both solutions in tensor memory (DESIGN.md "Next").
 #pragma once
 #include "fd1d_warp.cuh"
 
@@ -88,7 +95,6 @@ __global__ void __launch_bounds__(128, MINB) fd1d_warp_bs_kernel(const Fd1dBatch
 
     const uint32_t n_pde = batch_n_pde(B);
     const uint32_t n_grp = (n_pde + 3) / 4;
-    skew_start(B);
     for (uint32_t grp = blockIdx.x; grp < n_grp; grp += gridDim.x) {
         int levels = 5;
         double vr[NODES];  // the solution as given (projected when e = 1), this lane's 32 nodes

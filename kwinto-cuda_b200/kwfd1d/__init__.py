@@ -150,8 +150,8 @@ class Fd1dGpu_Pricer(Pricer):
     reference (src/Pricer/kwFd1d.cpp:12-16) plus FD1D.GPU.DEVICE (int), FD1D.GPU.LAYOUT
     ("auto"|"reg"|"soa"), FD1D.GPU.PRECISION ("f64"), FD1D.GPU.COMPRESS (int 0/1),
     FD1D.GPU.VARIANT (int), FD1D.GPU.EXACT (int 0/1/2: 0 lets provably negligible carry terms be
-    dropped, 2 keeps every term), FD1D.GPU.BS_FUSED (int 0/1/2, "FD1D-BS-GPU" only: 0 = the fused
-    American + European march where it applies, 1 = two separate solves, 2 = fused for every batch size)."""
+    dropped, 2 keeps every term), FD1D.GPU.BS_FUSED (int, "FD1D-BS-GPU" only: 0 = two solves as the
+    reference does, 2 = the fused American + European march of fd1d_warp_bs.cuh -- same prices, measured slower)."""
 
     _mode_bs = False
 

@@ -95,7 +95,7 @@ def test_fd1d_bs_fused_march(key):
     n_chain = len({(r["t"], r["r"], r["q"], r["z"], r["e"], r["w"]) for r in o})
     assert info["last_n_pde"] == n_chain
     assert maxdiff(got, g[key + "/fd1d_bs"]) <= TOL, maxdiff(got, g[key + "/fd1d_bs"])
-    two = make_pricer(t, x, mode="FD1D-BS-GPU", **{"FD1D.GPU.BS_FUSED": 1})
+    two = make_pricer(t, x, mode="FD1D-BS-GPU")
     err, got2 = two.price(o)
     assert err == "" and two.info()["variant"] != 251
     assert maxdiff(got2, g[key + "/fd1d_bs"]) <= TOL
@@ -119,17 +119,17 @@ def test_fd1d_bs_fused_range_error_and_dispatch():
     assert "not in range" in err and np.isnan(got[3])
     keep = np.arange(o.shape[0]) != 3
     assert maxdiff(got[keep], want[keep]) <= TOL
-    # auto dispatch: small batches take the two-solve path, a device wave or more the fused kernel
+    # the default is the two-solve path; the fused kernel is opt-in and refuses grids it has no tile for
     auto = make_pricer(64, 1024, mode="FD1D-BS-GPU")
-    err, small = auto.price(synthetic_options(64, 5))
-    assert err == "" and auto.info()["variant"] != 251
     big = synthetic_options(2048, 5, european_every=7)
     err, a = auto.price(big)
-    assert err == "" and auto.info()["variant"] == 251
-    two = make_pricer(64, 1024, mode="FD1D-BS-GPU", **{"FD1D.GPU.BS_FUSED": 1})
-    err, b = two.price(big)
-    assert err == "" and maxdiff(a, b) <= 1e-10
-    assert maxdiff(a[:64], small) <= 1e-10
+    assert err == "" and auto.info()["variant"] != 251
+    fused = make_pricer(64, 1024, mode="FD1D-BS-GPU", **{"FD1D.GPU.BS_FUSED": 2})
+    err, b = fused.price(big)
+    assert err == "" and fused.info()["variant"] == 251 and maxdiff(a, b) <= 1e-10
+    bad = make_pricer(64, 512, mode="FD1D-BS-GPU", **{"FD1D.GPU.BS_FUSED": 2})
+    err, _ = bad.price(big[:8])
+    assert "BS_FUSED" in err
 
 
 @pytest.mark.parametrize("layout", ["reg", "soa"])
