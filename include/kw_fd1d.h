@@ -80,11 +80,13 @@ typedef struct kw_fd1d_config {
     int32_t exact;       /* FD1D.GPU.EXACT: 0 (default) carry terms proven < 2^-56 may be    */
                          /* dropped (DESIGN.md "Truncation"); 1: keep all scan levels;       */
                          /* 2: keep every carry term                                         */
-    int32_t bs_fused;    /* FD1D.GPU.BS_FUSED, kw_fd1d_price_bs only: 0 or 1 (default) two solves, as the     */
-                         /* reference; 2: one launch marches the solution as given and its European copy    */
-                         /* side by side (fd1d_warp_bs.cuh; fp64, 512 < x <= 1024).  Bit-identical prices;   */
-                         /* measured SLOWER (0.40 M vs 0.56 M options/s at 1024^2: its 800-instruction step  */
-                         /* overflows the instruction cache), kept as a measured experiment      */
+    int32_t bs_fused;    /* FD1D.GPU.BS_FUSED, kw_fd1d_price_bs only.  0 (default): batches of a device wave  */
+                         /* or more (fp64, 512 < x <= 1024) are priced by ONE launch in which every warp     */
+                         /* marches its chain as given and then the European copy, with one set-up and one   */
+                         /* tensor-memory copy of the coefficients (variant 253); other batches: two solves, */
+                         /* as the reference.  1: always two solves.  4: variant 253 for every batch size.   */
+                         /* Measured experiments with the same prices: 3 = the two marches side  */
+                         /* by side in warps w and w + 4 (variant 252), 2 = both in one warp's step (251)    */
     int32_t reserved;
 } kw_fd1d_config;
 

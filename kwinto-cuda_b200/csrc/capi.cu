@@ -72,6 +72,11 @@ struct RegVariant {
         ID, KW_FD1D_F64, 8, 128, MINB_, false, false, fd1d_warp_kernel<4, MINB_, ICMP_, PAIR_>,    \
             WarpSmem<4>::bytes(), 256, 4                                                           \
     }
+#define KW_VARIANT_WRT(ID, MINB_)                                                                 \
+    {                                                                                              \
+        ID, KW_FD1D_F64, 8, 128, MINB_, false, false, fd1d_warp_kernel<4, MINB_, false, true, 0, true>, \
+            WarpSmem<4>::bytes(), 256, 4                                                           \
+    }
 #define KW_VARIANT_WN(ID, NCH_, MINB_)                                                            \
     {                                                                                              \
         ID, KW_FD1D_F64, 8, 32 * NCH_, MINB_, false, false, fd1d_warp_kernel<NCH_, MINB_, false, true>, \
@@ -120,6 +125,7 @@ const RegVariant g_variants[] = {
     KW_VARIANT_W(232, 2, true, false),
     KW_VARIANT_W(231, 2, false, false),  // one chunk at a time, next chunk's a~ prefetched
     KW_VARIANT_W(234, 2, true, true),
+    KW_VARIANT_WRT(235, 2),  // 233 with the scan-level count as a run-time value: one march loop instead of five
     KW_VARIANT_W2(241, 2, false),  // v in tensor memory, floor from shared memory
     KW_VARIANT_W2(242, 2, true),
     KW_VARIANT_WIDE(331, 2, false),            // x <= 2048: Layout W over two warps per PDE
@@ -137,9 +143,17 @@ const RegVariant g_variants[] = {
     KW_VARIANT_F32(1301, 8, 256, 2),
     KW_VARIANT_F32(1401, 8, 512, 1),
 };
-// fused FD1D-BS march (fd1d_warp_bs.cuh): the solution as given and its European copy in one warp
-const RegVariant g_bs_variant = {251, KW_FD1D_F64, 8, 128, 2, false, false, fd1d_warp_bs_kernel<2>,
-                                 Warp2Smem<4>::bytes(), 256, 4};
+// fused FD1D-BS marches (one set-up and one tensor-memory copy of a~, g~, D for the solve as given and the
+// solve of the European copy).  253 (default where it applies; fd1d_warp.cuh, BS = 2): every warp marches its
+// chain as given, then the European copy.  252 (FD1D.GPU.BS_FUSED = 3; BS = 1): eight warps per CTA, warp w
+// marches PDE w as given while warp w + 4 marches the European copy.  251 (FD1D.GPU.BS_FUSED = 2;
+// fd1d_warp_bs.cuh): both solutions in one warp's step (instruction-cache bound, slower than two solves).
+const RegVariant g_bs_variant = {252, KW_FD1D_F64, 8, 256, 1, false, false, fd1d_warp_kernel<4, 1, false, true, 1, true>,
+                                 WarpSmem<4, 256>::bytes(), 256, 4};
+const RegVariant g_bs2_variant = {253, KW_FD1D_F64, 8, 128, 2, false, false, fd1d_warp_kernel<4, 2, false, true, 2, true>,
+                                  WarpSmem<4>::bytes(), 256, 4};
+const RegVariant g_bs1_variant = {251, KW_FD1D_F64, 8, 128, 2, false, false, fd1d_warp_bs_kernel<2>,
+                                  Warp2Smem<4>::bytes(), 256, 4};
 constexpr int kNumVariants = sizeof(g_variants) / sizeof(g_variants[0]);
 constexpr int kMaxRegX = 4096;
 
@@ -286,6 +300,7 @@ struct kw_fd1d_handle {
     const RegVariant* var_bs = nullptr;     // fused FD1D-BS march, when the configuration has one
     int ctas_per_sm_bs = 0;
     int regs_bs = 0;
+    bool bs_forced = false;                 // FD1D.GPU.BS_FUSED = 2 / 3: fused for every batch size
     const RegVariant* last_var = nullptr;   // what the last batch ran
     int last_grid = 0;
     int launches = 0;  // kernels launched by the current / last price call
@@ -377,7 +392,7 @@ int launch_batch(kw_fd1d_handle* h, Fd1dBatch B, cudaStream_t st)
             return KW_FD1D_OK;
         }
         KW_CUDA(h, cudaEventRecord(h->ev0, st));
-        v->fn<<<grid, v->pdes_per_cta > 1 ? 128 : v->P, v->smem, st>>>(B);
+        v->fn<<<grid, v->pdes_per_cta > 1 ? std::max(128, v->P) : v->P, v->smem, st>>>(B);
         h->launches += 1;
         KW_CUDA(h, cudaEventRecord(h->ev1, st));
         h->ev_valid = true;
@@ -584,7 +599,7 @@ int prepare_variant(kw_fd1d_handle* h, const RegVariant* var, const cudaDevicePr
     KW_CUDA(h, cudaFuncGetAttributes(&fa, var->fn));
     regs = fa.numRegs;
     int occ = 0;
-    const int block = var->pdes_per_cta > 1 ? 128 : var->P;  // Layout W: four warps = four PDEs
+    const int block = var->pdes_per_cta > 1 ? std::max(128, var->P) : var->P;  // Layout W: four warps = four PDEs (eight: fused FD1D-BS)
     KW_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, var->fn, block, var->smem));
     if (occ < 1) return fail(h, KW_FD1D_ECUDA, "Fd1dGpu_Pricer::init: kernel variant does not fit on an SM");
     if (var->tmem_cols > 0) {
@@ -647,8 +662,8 @@ int kw_fd1d_create(const kw_fd1d_config* cfg, kw_fd1d_handle** out)
         return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::init: FD1D.T_GRID_SIZE must be >= 2 and FD1D.X_GRID_SIZE >= 3");
     if (!(cfg->density > 0) || !(cfg->scale > 0))
         return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::init: FD1D.DENSITY and FD1D.SCALE must be positive");
-    if (cfg->bs_fused < 0 || cfg->bs_fused > 2)
-        return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::init: FD1D.GPU.BS_FUSED must be 0 or 2");
+    if (cfg->bs_fused < 0 || cfg->bs_fused > 4)
+        return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::init: FD1D.GPU.BS_FUSED must be 0 ... 4");
     if (cfg->exact < 0 || cfg->exact > 2)
         return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::init: FD1D.GPU.EXACT must be 0, 1 or 2");
     if (cfg->precision != KW_FD1D_F64 && cfg->precision != KW_FD1D_F32)
@@ -689,8 +704,10 @@ int kw_fd1d_create(const kw_fd1d_config* cfg, kw_fd1d_handle** out)
             }
         }
         // fused FD1D-BS march: fp64, one Layout W tile of 4 chunks per lane
-        if (cfg->bs_fused == 2 && cfg->precision == KW_FD1D_F64 && cfg->x_grid_size > 512 && cfg->x_grid_size <= 1024) {
-            h->var_bs = &g_bs_variant;
+        if (cfg->bs_fused != 1 && cfg->precision == KW_FD1D_F64 && cfg->x_grid_size > 512 && cfg->x_grid_size <= 1024 &&
+            (cfg->variant == 0 || cfg->bs_fused >= 2)) {
+            h->var_bs = cfg->bs_fused == 2 ? &g_bs1_variant : (cfg->bs_fused == 3 ? &g_bs_variant : &g_bs2_variant);
+            h->bs_forced = cfg->bs_fused >= 2;
             if (int rc = prepare_variant(h, h->var_bs, prop, h->ctas_per_sm_bs, h->regs_bs)) return rc;
         }
     } else if (layout == KW_FD1D_LAYOUT_SOA) {
@@ -765,9 +782,11 @@ int kw_fd1d_price_bs(kw_fd1d_handle* h, const kw_option* assets, size_t n, doubl
     KW_CUDA(h, cudaSetDevice(h->cfg.device));
     KW_CUDA(h, h->d_prices.reserve(n));
     KW_CUDA(h, h->d_prices2.reserve(n));
-    if (h->cfg.bs_fused == 2 && !h->var_bs)
-        return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::price: FD1D.GPU.BS_FUSED = 2 needs fp64 and 512 < FD1D.X_GRID_SIZE <= 1024");
-    if (h->var_bs) {
+    if (h->cfg.bs_fused >= 2 && !h->var_bs)
+        return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::price: FD1D.GPU.BS_FUSED = 2 / 3 / 4 needs fp64 and 512 < FD1D.X_GRID_SIZE <= 1024");
+    // auto: fused from one full wave of the persistent grid (4 chains per CTA) upwards; below that the
+    // CTA-per-PDE kernel of the two-solve path spreads the batch over more SMs
+    if (h->var_bs && (h->bs_forced || n >= (size_t)h->sm_count * h->ctas_per_sm_bs * 4)) {
         // fused: the solve as given (:18) and the solve of the European copies (:21-28) are two value
         // vectors of the same chains marched by one launch; then + (BS - FD_euro) (:30-40)
         if (int rc = price_to_device(h, assets, n, h->d_opts, h->d_prices.p, h->d_prices2.p)) return rc;

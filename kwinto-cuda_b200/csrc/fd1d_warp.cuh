@@ -39,11 +39,11 @@
 
 namespace kwfd1d {
 
-template <int NCH>
+template <int NCH, int CTA = 128>
 struct WarpSmem {
     static constexpr int N = 8 * NCH * 32;  // nodes per PDE tile
     static constexpr int P = 32 * NCH;      // set-up threads per PDE
-    static constexpr int G = 128 / P;       // PDEs set up side by side
+    static constexpr int G = CTA / P;       // PDEs set up side by side
     // doubles: xs[4][N] | stage a, g, D, p, v [G][5][N] | chunk scalars A, G, R0 [G][3][P] | scratch [G][8*P]
     //          | misc [16] | per-warp scan constants [4][22][32]
     static constexpr size_t bytes()
@@ -54,11 +54,27 @@ struct WarpSmem {
 
 // PAIR: the chunk phase processes two chunks in lock step (two interleaved dependent chains per warp)
 // instead of one chunk at a time with its coefficients prefetched.
-template <int NCH, int MINB, bool ICMP, bool PAIR = false>
-__global__ void __launch_bounds__(128, MINB) fd1d_warp_kernel(const Fd1dBatch B)
+// BS: the fused march of the control-variate pricer "FD1D-BS" (Fd1d_BlackScholes_Pricer::price, reference
+// src/Pricer/kwFd1d_BlackScholes.cpp:15-43: the solve as given plus the solve of a European copy of every
+// chain).  Both solves share the grid and the hoisted LU, so ONE set-up and ONE tensor-memory copy of a~, g~,
+// D serve both; the European march has no floor loads, compares or selects (308 instead of 444 instructions
+// per step).  Prices go to B.prices (as given) and B.prices_eu (European); capi.cu adds the closed form.
+//   BS = 2 (variant 253): every warp marches its PDE as given, then re-creates the payoff from the x grid
+//           and marches the European copy with the coefficients still in tensor memory.  A chain that is
+//           given as European is marched once and priced into both arrays.
+//   BS = 1 (variant 252): EIGHT warps per CTA, warp w < 4 marches PDE w as given and warp w + 4 its European
+//           copy at the same time (shared TMEM lane quarter w, two PDEs set up side by side, one CTA per SM).
+//           Measured slower than BS = 2: the European warp finishes early and its partner runs on alone.
+// RT: the number of scan levels is a run-time value inside ONE march loop instead of five specialised
+// copies of it.  Warps of an SM then execute the same code whatever their PDE's level count: the SM's
+// instruction cache holds ~32 KB, a specialised step is 7 KB, and with BS there are two roles as well
+// (ncu stall_no_instruction 0.92 cycles per instruction with 6 hot loops per SM, profiles/r1_aw_*).
+template <int NCH, int MINB, bool ICMP, bool PAIR = false, int BS = 0, bool RT = false>
+__global__ void __launch_bounds__(BS == 1 ? 256 : 128, MINB) fd1d_warp_kernel(const Fd1dBatch B)
 {
     static_assert(NCH == 4 || (NCH == 2 && PAIR), "4 chunks per lane (512 < x <= 1024) or 2 (256 < x <= 512)");
-    using L = WarpSmem<NCH>;
+    static_assert(!BS || (NCH == 4 && PAIR && !ICMP && RT), "fused FD1D-BS march: chunk pairs, 512 < x <= 1024");
+    using L = WarpSmem<NCH, BS == 1 ? 256 : 128>;
     constexpr int N = L::N;
     constexpr int P = L::P;   // set-up threads per PDE (Layout B's cooperative set-up)
     constexpr int G = L::G;   // PDEs set up side by side by the CTA's 128 threads
@@ -74,7 +90,8 @@ __global__ void __launch_bounds__(128, MINB) fd1d_warp_kernel(const Fd1dBatch B)
     double* wconst = misc + 16;       // [4 warps][22][32 lanes] scan constants of the warp's PDE
 
     const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
+    const int warp = BS == 1 ? (threadIdx.x >> 5) & 3 : threadIdx.x >> 5;  // PDE of the group = TMEM lane quarter
+    const bool euro = BS == 1 && threadIdx.x >= 128;                       // BS = 1: the European copy's warp
     const int sg = threadIdx.x / P;   // set-up group of this thread
     const int k = threadIdx.x % P;    // its chunk in the group's PDE
     const int xDim = B.xDim;
@@ -87,7 +104,7 @@ __global__ void __launch_bounds__(128, MINB) fd1d_warp_kernel(const Fd1dBatch B)
 
     // tensor memory: 4 arrays x 8*NCH doubles per lane = 64*NCH columns per warp
     __shared__ uint32_t s_taddr;
-    if (warp == 0) tmem::alloc<64 * NCH>(smem_addr(&s_taddr));
+    if (threadIdx.x < 32) tmem::alloc<64 * NCH>(smem_addr(&s_taddr));
     tmem::fence_before();
     __syncthreads();
     tmem::fence_after();
@@ -100,7 +117,7 @@ __global__ void __launch_bounds__(128, MINB) fd1d_warp_kernel(const Fd1dBatch B)
         double vr[NODES];              // this lane's nodes of PDE 4*grp + warp
         double Ac[NCH], Gc[NCH], R0c[NCH];
         double bmax_mine = 1.;
-        bool put_mine = true;
+        bool put_mine = true, amer_mine = true;
 
         // ---------------- set-up: G PDEs at a time, P threads each --------------------------------
         for (int q0 = 0; q0 < 4; q0 += G) {
@@ -157,11 +174,13 @@ __global__ void __launch_bounds__(128, MINB) fd1d_warp_kernel(const Fd1dBatch B)
                 for (int c = 0; c < NCH; ++c) {
                     const int ch = lane * NCH + c;
                     double t8[8];
+                    if (!euro) {
 #pragma unroll
-                    for (int arr = 0; arr < 4; ++arr) {
+                        for (int arr = 0; arr < 4; ++arr) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) t8[i] = st[arr * N + ch * 8 + i];
-                        tmem::st8(tbase + 16 * NCH * arr + 16 * c, t8);
+                            for (int i = 0; i < 8; ++i) t8[i] = st[arr * N + ch * 8 + i];
+                            tmem::st8(tbase + 16 * NCH * arr + 16 * c, t8);
+                        }
                     }
 #pragma unroll
                     for (int i = 0; i < 8; ++i) vr[8 * c + i] = st[4 * N + ch * 8 + i];
@@ -169,14 +188,16 @@ __global__ void __launch_bounds__(128, MINB) fd1d_warp_kernel(const Fd1dBatch B)
                     Gc[c] = st_G[ch];
                     R0c[c] = st_R0[ch];
                 }
-                tmem::wait_st();
+                if (!euro) tmem::wait_st();
                 double bm = scr[0];
 #pragma unroll
                 for (int w = 1; w < P / 32; ++w) bm = fmax(bm, scr[w]);
                 bmax_mine = bm;
                 // the owner's PDE may differ from the one this thread helped to set up: read its flag directly
                 const uint32_t rep_own = B.pde_rep ? __ldg(B.pde_rep + 4 * grp + warp) : 4 * grp + warp;
-                put_mine = load_option(B.opts + rep_own).w < 0;
+                const kw_option own = load_option(B.opts + rep_own);
+                put_mine = own.w < 0;
+                amer_mine = own.e != 0;
             }
             __syncthreads();
         }
@@ -233,23 +254,32 @@ __global__ void __launch_bounds__(128, MINB) fd1d_warp_kernel(const Fd1dBatch B)
             // and re-read every step: registers are for v, one chunk's sweeps and the coefficient
             // stage (current chunk + the prefetched next one).
             double* wc = wconst + warp * (22 * 32) + lane;
+            if (!euro) {
 #pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-                wc[(0 + c) * 32] = Ac[c];
-                wc[(4 + c) * 32] = Gc[c];
-                wc[(8 + c) * 32] = R0c[c];
-            }
+                for (int c = 0; c < NCH; ++c) {
+                    wc[(0 + c) * 32] = Ac[c];
+                    wc[(4 + c) * 32] = Gc[c];
+                    wc[(8 + c) * 32] = R0c[c];
+                }
 #pragma unroll
-            for (int d = 0; d < 5; ++d) {
-                wc[(12 + d) * 32] = AfL[d];
-                wc[(17 + d) * 32] = GbL[d];
+                for (int d = 0; d < 5; ++d) {
+                    wc[(12 + d) * 32] = AfL[d];
+                    wc[(17 + d) * 32] = GbL[d];
+                }
             }
             __syncwarp();
+            if constexpr (BS == 1) {
+                // the European warp reads its partner's tensor-memory arrays and scan constants
+                tmem::fence_before();
+                asm volatile("bar.sync %0, 64;" ::"r"(warp + 1) : "memory");
+                tmem::fence_after();
+            }
             const uint32_t a_wc = smem_addr(wc);
             auto K = [&](int idx) { return lds_f64(a_wc + idx * 256); };
 
-            auto march = [&](auto lev_c) {
+            auto march = [&](auto lev_c, auto euro_c) {
                 constexpr int LEV = decltype(lev_c)::value;
+                constexpr bool EURO = decltype(euro_c)::value;  // European copy: no floor, no compare
                 double e[NCH], f[NCH];
                 // local sweeps of chunk c from zero: e = last forward value, f = first backward value
                 auto local = [&](const double (&a8)[8], const double (&g8)[8], int c) {
@@ -279,10 +309,29 @@ __global__ void __launch_bounds__(128, MINB) fd1d_warp_kernel(const Fd1dBatch B)
                     double S = e[0];
 #pragma unroll
                     for (int c = 1; c < NCH; ++c) S = fma(K(c), S, e[c]);
+                    if constexpr (LEV > 0) {
 #pragma unroll
-                    for (int d = 0; d < LEV; ++d) {
-                        const double o = __shfl_up_sync(FULL, S, 1 << d);
-                        S = fma(K(12 + d), o, S);
+                        for (int d = 0; d < LEV; ++d) {
+                            const double o = __shfl_up_sync(FULL, S, 1 << d);
+                            S = fma(K(12 + d), o, S);
+                        }
+                    } else {
+                        // run-time level count (warp-uniform, 1..5): nested so that the usual 1-3 levels skip the rest
+                        auto up = [&](int d) {
+                            const double o = __shfl_up_sync(FULL, S, 1 << d);
+                            S = fma(K(12 + d), o, S);
+                        };
+                        up(0);
+                        if (levels > 1) {
+                            up(1);
+                            if (levels > 2) {
+                                up(2);
+                                if (levels > 3) {
+                                    up(3);
+                                    if (levels > 4) up(4);
+                                }
+                            }
+                        }
                     }
                     double Yin[NCH];
                     {
@@ -297,10 +346,28 @@ __global__ void __launch_bounds__(128, MINB) fd1d_warp_kernel(const Fd1dBatch B)
                     double T = f[NCH - 1];
 #pragma unroll
                     for (int c = NCH - 2; c >= 0; --c) T = fma(K(4 + c), T, f[c]);
+                    if constexpr (LEV > 0) {
 #pragma unroll
-                    for (int d = 0; d < LEV; ++d) {
-                        const double o = __shfl_down_sync(FULL, T, 1 << d);
-                        T = fma(K(17 + d), o, T);
+                        for (int d = 0; d < LEV; ++d) {
+                            const double o = __shfl_down_sync(FULL, T, 1 << d);
+                            T = fma(K(17 + d), o, T);
+                        }
+                    } else {
+                        auto down = [&](int d) {
+                            const double o = __shfl_down_sync(FULL, T, 1 << d);
+                            T = fma(K(17 + d), o, T);
+                        };
+                        down(0);
+                        if (levels > 1) {
+                            down(1);
+                            if (levels > 2) {
+                                down(2);
+                                if (levels > 3) {
+                                    down(3);
+                                    if (levels > 4) down(4);
+                                }
+                            }
+                        }
                     }
                     double Uin[NCH];
                     {
@@ -324,8 +391,10 @@ __global__ void __launch_bounds__(128, MINB) fd1d_warp_kernel(const Fd1dBatch B)
                             KW_W_LD8(tbase + T_G + 16 * cB, gB);
                             KW_W_LD8(tbase + T_D + 16 * cA, dA);
                             KW_W_LD8(tbase + T_D + 16 * cB, dB);
-                            KW_W_LD8(tbase + T_P + 16 * cA, pA);
-                            KW_W_LD8(tbase + T_P + 16 * cB, pB);
+                            if constexpr (!EURO) {
+                                KW_W_LD8(tbase + T_P + 16 * cA, pA);
+                                KW_W_LD8(tbase + T_P + 16 * cB, pB);
+                            }
                             double yA[8], yB[8];
                             yA[0] = fma(aA[0], Yin[cA], vr[8 * cA]);
                             yB[0] = fma(aB[0], Yin[cB], vr[8 * cB]);
@@ -338,8 +407,10 @@ __global__ void __launch_bounds__(128, MINB) fd1d_warp_kernel(const Fd1dBatch B)
                             tmem::wait_ld_dep(gB);
                             tmem::wait_ld_dep(dA);
                             tmem::wait_ld_dep(dB);
-                            tmem::wait_ld_dep(pA);
-                            tmem::wait_ld_dep(pB);
+                            if constexpr (!EURO) {
+                                tmem::wait_ld_dep(pA);
+                                tmem::wait_ld_dep(pB);
+                            }
                             double uA = Uin[cA], uB = Uin[cB];
 #pragma unroll
                             for (int i = 7; i >= 0; --i) {
@@ -347,8 +418,13 @@ __global__ void __launch_bounds__(128, MINB) fd1d_warp_kernel(const Fd1dBatch B)
                                 uB = fma(gB[i], uB, yB[i]);
                                 const double rA = fma(dA[i], uA, -vr[8 * cA + i]);
                                 const double rB = fma(dB[i], uB, -vr[8 * cB + i]);
-                                vr[8 * cA + i] = ICMP ? max_like_icmp(rA, pA[i]) : max_like_std(rA, pA[i]);
-                                vr[8 * cB + i] = ICMP ? max_like_icmp(rB, pB[i]) : max_like_std(rB, pB[i]);
+                                if constexpr (EURO) {
+                                    vr[8 * cA + i] = rA;
+                                    vr[8 * cB + i] = rB;
+                                } else {
+                                    vr[8 * cA + i] = ICMP ? max_like_icmp(rA, pA[i]) : max_like_std(rA, pA[i]);
+                                    vr[8 * cB + i] = ICMP ? max_like_icmp(rB, pB[i]) : max_like_std(rB, pB[i]);
+                                }
                             }
                             // next step's local sweeps of both chunks, interleaved
                             yA[0] = vr[8 * cA];
@@ -403,38 +479,64 @@ __global__ void __launch_bounds__(128, MINB) fd1d_warp_kernel(const Fd1dBatch B)
                 }
                 tmem::wait_ld_dep(an);  // nothing in flight when the arrays are rewritten
             };
-            switch (levels) {
-                case 1: march(std::integral_constant<int, 1>{}); break;
-                case 2: march(std::integral_constant<int, 2>{}); break;
-                case 3: march(std::integral_constant<int, 3>{}); break;
-                case 4: march(std::integral_constant<int, 4>{}); break;
-                default: march(std::integral_constant<int, 5>{}); break;
+            if constexpr (RT) {
+                if (euro)
+                    march(std::integral_constant<int, 0>{}, std::integral_constant<bool, BS == 1>{});
+                else
+                    march(std::integral_constant<int, 0>{}, std::false_type{});
+            } else {
+                switch (levels) {
+                    case 1: march(std::integral_constant<int, 1>{}, std::false_type{}); break;
+                    case 2: march(std::integral_constant<int, 2>{}, std::false_type{}); break;
+                    case 3: march(std::integral_constant<int, 3>{}, std::false_type{}); break;
+                    case 4: march(std::integral_constant<int, 4>{}, std::false_type{}); break;
+                    default: march(std::integral_constant<int, 5>{}, std::false_type{}); break;
+                }
             }
-            if (lane == 0) {
+            if (lane == 0 && !euro) {
                 // histogram buckets shared with Layout B: 0 = exact requested, 1 = all 5 levels, 2/3/4 = 4/3/2, 5 = 1 level
                 const int bucket = B.max_mode == 0 ? 0 : (levels == 5 ? 1 : 6 - levels);
                 atomicAdd(&B.status[2 + bucket], 1u);
             }
             // ---------------- epilogue: interpolate every option of this chain -------------------
-            double* vfin = st_all + warp * N;  // the stage is free: set-up finished before the march
+            double* vfin = st_all + (warp + (euro ? 4 : 0)) * N;  // the stage is free: set-up finished before the march
+            const double* x = xs + warp * N;
+            auto emit = [&](double* out) {
 #pragma unroll
-            for (int i = 0; i < NODES; ++i) vfin[lane * NODES + i] = vr[i];
-            __syncwarp();
-            {
-                const double* x = xs + warp * N;
+                for (int i = 0; i < NODES; ++i) vfin[lane * NODES + i] = vr[i];
+                __syncwarp();
+                Fd1dBatch Bo = B;
+                Bo.prices = out;
                 uint32_t q0, q1;
                 chain_range(B, my_pde, q0, q1);
                 for (uint32_t q = q0 + lane; q < q1; q += 32) {
                     const uint32_t oi = B.csr_opt ? __ldg(B.csr_opt + q) : q;
-                    price_option(B, oi, [&](int j) { return x[j]; }, [&](int j) { return vfin[j]; });
+                    price_option(Bo, oi, [&](int j) { return x[j]; }, [&](int j) { return vfin[j]; });
                 }
+                __syncwarp();  // vfin is rewritten by the next emit
+            };
+            emit(euro ? B.prices_eu : B.prices);
+            if constexpr (BS == 2) {
+                if (amer_mine) {
+                    // the European copy: payoff again (src/Pricer/kwFd1d.cpp:127-139, as in setup_lu), same LU
+                    // (still in tensor memory), no projection
+#pragma unroll
+                    for (int i = 0; i < NODES; ++i) {
+                        const int j = lane * NODES + i;
+                        vr[i] = j < xDim ? payoff_node(put_mine, x[j]) : 0.;
+                    }
+                    march(std::integral_constant<int, 0>{}, std::true_type{});
+                }
+                emit(B.prices_eu);  // a chain given as European: one march, both arrays
             }
         }
-        __syncthreads();  // stage and x grids are rewritten by the next group
+        if constexpr (BS == 1) tmem::fence_before();  // the partner's tcgen05.ld of this group are complete
+        __syncthreads();  // stage, x grids and tensor memory are rewritten by the next group
+        if constexpr (BS == 1) tmem::fence_after();
     }
     tmem::fence_before();
     __syncthreads();
-    if (warp == 0) tmem::dealloc<64 * NCH>(s_taddr);
+    if (threadIdx.x < 32) tmem::dealloc<64 * NCH>(s_taddr);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -150,8 +150,9 @@ class Fd1dGpu_Pricer(Pricer):
     reference (src/Pricer/kwFd1d.cpp:12-16) plus FD1D.GPU.DEVICE (int), FD1D.GPU.LAYOUT
     ("auto"|"reg"|"soa"), FD1D.GPU.PRECISION ("f64"), FD1D.GPU.COMPRESS (int 0/1),
     FD1D.GPU.VARIANT (int), FD1D.GPU.EXACT (int 0/1/2: 0 lets provably negligible carry terms be
-    dropped, 2 keeps every term), FD1D.GPU.BS_FUSED (int, "FD1D-BS-GPU" only: 0 = two solves as the
-    reference does, 2 = the fused American + European march of fd1d_warp_bs.cuh -- same prices, measured slower)."""
+    dropped, 2 keeps every term), FD1D.GPU.BS_FUSED (int, "FD1D-BS-GPU" only: 0 = fused
+    American + European march (variant 253) for batches of a device wave or more, 1 = always two solves as
+    the reference does, 4 = variant 253 for every batch size, 3 / 2 = the measured experiments 252 / 251)."""
 
     _mode_bs = False
 

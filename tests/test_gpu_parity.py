@@ -79,28 +79,31 @@ def test_synthetic_golden_all_shapes():
     assert err == "" and maxdiff(got, g["bs_mix/fd1d_bs"]) <= TOL
 
 
+@pytest.mark.parametrize("fused,variant", [(4, 253), (3, 252), (2, 251)])
 @pytest.mark.parametrize("key", ["bs_1024", "bs_700x200", "bs_513x64"])
-def test_fd1d_bs_fused_march(key):
-    # src/Pricer/kwFd1d_BlackScholes.cpp:15-43 with both solves of a chain marched by one launch
-    # (fd1d_warp_bs.cuh, variant 251): against the reference's FD1D-BS prices and against the
-    # two-solve path of the same library
+def test_fd1d_bs_fused_march(key, fused, variant):
+    # src/Pricer/kwFd1d_BlackScholes.cpp:15-43 with both solves of a chain marched by one launch --
+    # variant 253: every warp marches its chain as given, then the European copy (fd1d_warp.cuh, BS = 2);
+    # variant 252: warp w marches the chain as given, warp w + 4 its European copy (BS = 1);
+    # variant 251: both in one warp's step (fd1d_warp_bs.cuh) -- against the reference's FD1D-BS prices
+    # and against the two-solve path of the same library
     g = load_golden("bs_fused")
     t, x = (int(v) for v in g[key + "/grid"])
     o = g[key + "/options"]
-    fused = make_pricer(t, x, mode="FD1D-BS-GPU", **{"FD1D.GPU.BS_FUSED": 2})
-    err, got = fused.price(o)
+    p = make_pricer(t, x, mode="FD1D-BS-GPU", **{"FD1D.GPU.BS_FUSED": fused})
+    err, got = p.price(o)
     assert err == "", err
-    info = fused.info()
-    assert info["variant"] == 251, info
+    info = p.info()
+    assert info["variant"] == variant, info
     n_chain = len({(r["t"], r["r"], r["q"], r["z"], r["e"], r["w"]) for r in o})
     assert info["last_n_pde"] == n_chain
     assert maxdiff(got, g[key + "/fd1d_bs"]) <= TOL, maxdiff(got, g[key + "/fd1d_bs"])
-    two = make_pricer(t, x, mode="FD1D-BS-GPU")
+    two = make_pricer(t, x, mode="FD1D-BS-GPU", **{"FD1D.GPU.BS_FUSED": 1})
     err, got2 = two.price(o)
-    assert err == "" and two.info()["variant"] != 251
+    assert err == "" and two.info()["variant"] not in (251, 252, 253)
     assert maxdiff(got2, g[key + "/fd1d_bs"]) <= TOL
     assert maxdiff(got, got2) <= 1e-10
-    # the same handle still prices plain FD1D through kw_fd1d_price with the default kernel
+    # a plain FD1D pricer of the same configuration is unaffected
     plain = make_pricer(t, x)
     err, gotp = plain.price(o)
     assert err == "" and maxdiff(gotp, g[key + "/fd1d"]) <= TOL
@@ -114,20 +117,31 @@ def test_fd1d_bs_fused_range_error_and_dispatch():
     o = g["bs_700x200/options"].copy()
     want = g["bs_700x200/fd1d_bs"]
     o["s"][3] = 1e9
-    p = make_pricer(200, 700, mode="FD1D-BS-GPU", **{"FD1D.GPU.BS_FUSED": 2})
-    err, got = p.price(o)
-    assert "not in range" in err and np.isnan(got[3])
-    keep = np.arange(o.shape[0]) != 3
-    assert maxdiff(got[keep], want[keep]) <= TOL
-    # the default is the two-solve path; the fused kernel is opt-in and refuses grids it has no tile for
+    for fused in (4, 3, 2):
+        p = make_pricer(200, 700, mode="FD1D-BS-GPU", **{"FD1D.GPU.BS_FUSED": fused})
+        err, got = p.price(o)
+        assert "not in range" in err and np.isnan(got[3])
+        keep = np.arange(o.shape[0]) != 3
+        assert maxdiff(got[keep], want[keep]) <= TOL
+    # auto dispatch: small batches take the two-solve path, a device wave or more the fused kernel
     auto = make_pricer(64, 1024, mode="FD1D-BS-GPU")
+    small_o = synthetic_options(64, 5, european_every=7)
+    err, small = auto.price(small_o)
+    assert err == "" and auto.info()["variant"] not in (251, 252, 253)
     big = synthetic_options(2048, 5, european_every=7)
     err, a = auto.price(big)
-    assert err == "" and auto.info()["variant"] != 251
-    fused = make_pricer(64, 1024, mode="FD1D-BS-GPU", **{"FD1D.GPU.BS_FUSED": 2})
-    err, b = fused.price(big)
-    assert err == "" and fused.info()["variant"] == 251 and maxdiff(a, b) <= 1e-10
-    bad = make_pricer(64, 512, mode="FD1D-BS-GPU", **{"FD1D.GPU.BS_FUSED": 2})
+    assert err == "" and auto.info()["variant"] == 253
+    two = make_pricer(64, 1024, mode="FD1D-BS-GPU", **{"FD1D.GPU.BS_FUSED": 1})
+    err, b = two.price(big)
+    assert err == "" and two.info()["variant"] not in (251, 252, 253) and maxdiff(a, b) <= 1e-10
+    assert maxdiff(a[:64], small) <= 1e-10
+    # a ragged last group (n % 4 != 0) and a batch of one
+    for fused in (4, 3):
+        for n in (1, 5, 2049):
+            err, c = make_pricer(64, 1024, mode="FD1D-BS-GPU", **{"FD1D.GPU.BS_FUSED": fused}).price(big[:n])
+            assert err == "" and maxdiff(c, b[:n]) <= 1e-10, (fused, n)
+    # the fused kernels have no tile for other grids
+    bad = make_pricer(64, 512, mode="FD1D-BS-GPU", **{"FD1D.GPU.BS_FUSED": 4})
     err, _ = bad.price(big[:8])
     assert "BS_FUSED" in err
 
@@ -144,7 +158,7 @@ def test_layouts_agree_with_reference(layout):
         assert maxdiff(got, g[k + "/fd1d"]) <= TOL, (layout, k)
 
 
-@pytest.mark.parametrize("variant", [201, 202, 203, 204, 205, 211, 213, 221, 222, 231, 232, 233, 234, 241, 242])
+@pytest.mark.parametrize("variant", [201, 202, 203, 204, 205, 211, 213, 221, 222, 231, 232, 233, 234, 235, 241, 242])
 def test_all_1024_variants(variant):
     g, _ = synthetic_cases()
     p = make_pricer(1024, 1024, **{"FD1D.GPU.VARIANT": variant})
