@@ -152,6 +152,8 @@ const RegVariant g_bs_variant = {252, KW_FD1D_F64, 8, 256, 1, false, false, fd1d
                                  WarpSmem<4, 256>::bytes(), 256, 4};
 const RegVariant g_bs2_variant = {253, KW_FD1D_F64, 8, 128, 2, false, false, fd1d_warp_kernel<4, 2, false, true, 2, true>,
                                   WarpSmem<4>::bytes(), 256, 4};
+const RegVariant g_bs2n2_variant = {153, KW_FD1D_F64, 8, 64, 2, false, false, fd1d_warp_kernel<2, 2, false, true, 2, true>,
+                                    WarpSmem<2>::bytes(), 128, 4};  // 256 < x <= 512, two chunks per lane
 const RegVariant g_bs1_variant = {251, KW_FD1D_F64, 8, 128, 2, false, false, fd1d_warp_bs_kernel<2>,
                                   Warp2Smem<4>::bytes(), 256, 4};
 constexpr int kNumVariants = sizeof(g_variants) / sizeof(g_variants[0]);
@@ -704,9 +706,13 @@ int kw_fd1d_create(const kw_fd1d_config* cfg, kw_fd1d_handle** out)
             }
         }
         // fused FD1D-BS march: fp64, one Layout W tile of 4 chunks per lane
-        if (cfg->bs_fused != 1 && cfg->precision == KW_FD1D_F64 && cfg->x_grid_size > 512 && cfg->x_grid_size <= 1024 &&
+        const bool tile4 = cfg->x_grid_size > 512 && cfg->x_grid_size <= 1024;
+        const bool tile2 = cfg->x_grid_size > 256 && cfg->x_grid_size <= 512;
+        const bool seq = cfg->bs_fused == 0 || cfg->bs_fused == 4;  // variant 253 / 153
+        if (cfg->bs_fused != 1 && cfg->precision == KW_FD1D_F64 && (tile4 || (tile2 && seq)) &&
             (cfg->variant == 0 || cfg->bs_fused >= 2)) {
-            h->var_bs = cfg->bs_fused == 2 ? &g_bs1_variant : (cfg->bs_fused == 3 ? &g_bs_variant : &g_bs2_variant);
+            h->var_bs = cfg->bs_fused == 2 ? &g_bs1_variant
+                                           : (cfg->bs_fused == 3 ? &g_bs_variant : (tile4 ? &g_bs2_variant : &g_bs2n2_variant));
             h->bs_forced = cfg->bs_fused >= 2;
             if (int rc = prepare_variant(h, h->var_bs, prop, h->ctas_per_sm_bs, h->regs_bs)) return rc;
         }
@@ -783,7 +789,7 @@ int kw_fd1d_price_bs(kw_fd1d_handle* h, const kw_option* assets, size_t n, doubl
     KW_CUDA(h, h->d_prices.reserve(n));
     KW_CUDA(h, h->d_prices2.reserve(n));
     if (h->cfg.bs_fused >= 2 && !h->var_bs)
-        return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::price: FD1D.GPU.BS_FUSED = 2 / 3 / 4 needs fp64 and 512 < FD1D.X_GRID_SIZE <= 1024");
+        return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::price: FD1D.GPU.BS_FUSED = 2 / 3 needs fp64 and 512 < FD1D.X_GRID_SIZE <= 1024, = 4 fp64 and 256 < FD1D.X_GRID_SIZE <= 1024");
     // auto: fused from one full wave of the persistent grid (4 chains per CTA) upwards; below that the
     // CTA-per-PDE kernel of the two-solve path spreads the batch over more SMs
     if (h->var_bs && (h->bs_forced || n >= (size_t)h->sm_count * h->ctas_per_sm_bs * 4)) {

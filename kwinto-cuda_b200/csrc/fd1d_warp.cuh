@@ -73,7 +73,8 @@ template <int NCH, int MINB, bool ICMP, bool PAIR = false, int BS = 0, bool RT =
 __global__ void __launch_bounds__(BS == 1 ? 256 : 128, MINB) fd1d_warp_kernel(const Fd1dBatch B)
 {
     static_assert(NCH == 4 || (NCH == 2 && PAIR), "4 chunks per lane (512 < x <= 1024) or 2 (256 < x <= 512)");
-    static_assert(!BS || (NCH == 4 && PAIR && !ICMP && RT), "fused FD1D-BS march: chunk pairs, 512 < x <= 1024");
+    static_assert(!BS || (PAIR && !ICMP && RT), "fused FD1D-BS march: chunk pairs, run-time scan levels");
+    static_assert(BS != 1 || NCH == 4, "BS = 1 (European copy in warp w + 4): 512 < x <= 1024 only");
     using L = WarpSmem<NCH, BS == 1 ? 256 : 128>;
     constexpr int N = L::N;
     constexpr int P = L::P;   // set-up threads per PDE (Layout B's cooperative set-up)

@@ -40,6 +40,9 @@ def main():
         ("bs_1024", with_chain_members(synthetic_options(1200, 21, european_every=5, call_every=3), 4, 1), 1024, 1024),
         ("bs_700x200", with_chain_members(synthetic_options(160, 22, european_every=3, call_every=2), 3, 2), 200, 700),
         ("bs_513x64", synthetic_options(40, 23, european_every=4, call_every=2), 64, 513),
+        # the two-chunk tile (256 < x <= 512), incl. the reference's default grid 512 x 512
+        ("bs_512", with_chain_members(synthetic_options(1300, 24, european_every=6, call_every=4), 5, 3), 512, 512),
+        ("bs_300x100", with_chain_members(synthetic_options(90, 25, european_every=3, call_every=2), 3, 4), 100, 300),
     ]
     for key, o, t, x in cases:
         out[key + "/options"] = o

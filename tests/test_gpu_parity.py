@@ -79,11 +79,13 @@ def test_synthetic_golden_all_shapes():
     assert err == "" and maxdiff(got, g["bs_mix/fd1d_bs"]) <= TOL
 
 
-@pytest.mark.parametrize("fused,variant", [(4, 253), (3, 252), (2, 251)])
-@pytest.mark.parametrize("key", ["bs_1024", "bs_700x200", "bs_513x64"])
+@pytest.mark.parametrize("key,fused,variant", [(k, f, v) for k in ("bs_1024", "bs_700x200", "bs_513x64")
+                                               for f, v in ((4, 253), (3, 252), (2, 251))] +
+                         [(k, 4, 153) for k in ("bs_512", "bs_300x100")])
 def test_fd1d_bs_fused_march(key, fused, variant):
     # src/Pricer/kwFd1d_BlackScholes.cpp:15-43 with both solves of a chain marched by one launch --
-    # variant 253: every warp marches its chain as given, then the European copy (fd1d_warp.cuh, BS = 2);
+    # variant 253 (153 for 256 < x <= 512): every warp marches its chain as given, then the European copy
+    # (fd1d_warp.cuh, BS = 2);
     # variant 252: warp w marches the chain as given, warp w + 4 its European copy (BS = 1);
     # variant 251: both in one warp's step (fd1d_warp_bs.cuh) -- against the reference's FD1D-BS prices
     # and against the two-solve path of the same library
@@ -100,7 +102,7 @@ def test_fd1d_bs_fused_march(key, fused, variant):
     assert maxdiff(got, g[key + "/fd1d_bs"]) <= TOL, maxdiff(got, g[key + "/fd1d_bs"])
     two = make_pricer(t, x, mode="FD1D-BS-GPU", **{"FD1D.GPU.BS_FUSED": 1})
     err, got2 = two.price(o)
-    assert err == "" and two.info()["variant"] not in (251, 252, 253)
+    assert err == "" and two.info()["variant"] not in (153, 251, 252, 253)
     assert maxdiff(got2, g[key + "/fd1d_bs"]) <= TOL
     assert maxdiff(got, got2) <= 1e-10
     # a plain FD1D pricer of the same configuration is unaffected
@@ -140,8 +142,12 @@ def test_fd1d_bs_fused_range_error_and_dispatch():
         for n in (1, 5, 2049):
             err, c = make_pricer(64, 1024, mode="FD1D-BS-GPU", **{"FD1D.GPU.BS_FUSED": fused}).price(big[:n])
             assert err == "" and maxdiff(c, b[:n]) <= 1e-10, (fused, n)
+    # the reference's default grid with the default keys: fused from a device wave upwards
+    d512 = make_pricer(mode="FD1D-BS-GPU")
+    err, c = d512.price(g["bs_512/options"])
+    assert err == "" and d512.info()["variant"] == 153 and maxdiff(c, g["bs_512/fd1d_bs"]) <= TOL
     # the fused kernels have no tile for other grids
-    bad = make_pricer(64, 512, mode="FD1D-BS-GPU", **{"FD1D.GPU.BS_FUSED": 4})
+    bad = make_pricer(64, 256, mode="FD1D-BS-GPU", **{"FD1D.GPU.BS_FUSED": 4})
     err, _ = bad.price(big[:8])
     assert "BS_FUSED" in err
 

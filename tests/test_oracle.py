@@ -85,7 +85,7 @@ def test_bs_fused_golden_bitexact(oracle):
     # the fixtures of the fused FD1D-BS march (tests/golden/make_golden_bs.py): chains with several
     # members, American / European, puts / calls; src/Pricer/kwFd1d_BlackScholes.cpp:15-43
     g = np.load(__import__("os").path.join(__import__("conftest").GOLDEN, "bs_fused.npz"))
-    for key in ("bs_700x200", "bs_513x64"):
+    for key in ("bs_700x200", "bs_513x64", "bs_300x100"):
         t, x = (int(v) for v in g[key + "/grid"])
         for mode, name in (("FD1D-BS", "fd1d_bs"), ("FD1D", "fd1d")):
             p, err = oracle.fd1d(g[key + "/options"], t, x, mode=mode)

@@ -52,6 +52,19 @@ def main():
               % (fused, p.info()["variant"], ["%.2f" % (1e3 * w) for w in wall], ["%.3f" % m for m in ms],
                  n / min(wall) / 1e6), flush=True)
         p.close()
+    for fused in (1, 4):
+        p = pricer("FD1D-BS-GPU", 512, 512, **{"FD1D.GPU.BS_FUSED": fused})
+        wall = []
+        for _ in range(4):
+            t0 = time.perf_counter()
+            err, got = p.price(opts)
+            wall.append(time.perf_counter() - t0)
+            assert err == ""
+        res[10 + fused] = got
+        print("FD1D-BS 512x512 fused=%d variant %d  wall ms %s -> %.4f M options/s"
+              % (fused, p.info()["variant"], ["%.2f" % (1e3 * w) for w in wall], n / min(wall) / 1e6), flush=True)
+        p.close()
+    print("512x512 fused vs two solves maxdiff %.2e" % float(np.max(np.abs(res[11] - res[14]))))
     print("FD1D-BS fused vs two solves maxdiff %.2e" % max(float(np.max(np.abs(res[1] - res[3]))), float(np.max(np.abs(res[1] - res[4])))))
 
 
