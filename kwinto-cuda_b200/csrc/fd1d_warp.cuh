@@ -386,8 +386,7 @@ __global__ void __launch_bounds__(BS == 1 ? 256 : 128, MINB) fd1d_warp_kernel(co
                             double aA[8], aB[8], gA[8], gB[8], dA[8], dB[8], pA[8], pB[8];
                             KW_W_LD8(tbase + T_A + 16 * cA, aA);
                             KW_W_LD8(tbase + T_A + 16 * cB, aB);
-                            tmem::wait_ld_dep(aA);
-                            tmem::wait_ld_dep(aB);
+                            tmem::hot_wait(aA, aB);
                             KW_W_LD8(tbase + T_G + 16 * cA, gA);
                             KW_W_LD8(tbase + T_G + 16 * cB, gB);
                             KW_W_LD8(tbase + T_D + 16 * cA, dA);
@@ -404,13 +403,12 @@ __global__ void __launch_bounds__(BS == 1 ? 256 : 128, MINB) fd1d_warp_kernel(co
                                 yA[i] = fma(aA[i], yA[i - 1], vr[8 * cA + i]);
                                 yB[i] = fma(aB[i], yB[i - 1], vr[8 * cB + i]);
                             }
-                            tmem::wait_ld_dep(gA);
-                            tmem::wait_ld_dep(gB);
-                            tmem::wait_ld_dep(dA);
-                            tmem::wait_ld_dep(dB);
                             if constexpr (!EURO) {
-                                tmem::wait_ld_dep(pA);
-                                tmem::wait_ld_dep(pB);
+                                tmem::hot_wait(gA, gB, dA);
+                                tmem::hot_wait(dB, pA, pB);
+                            } else {
+                                tmem::hot_wait(gA, gB);
+                                tmem::hot_wait(dA, dB);
                             }
                             double uA = Uin[cA], uB = Uin[cB];
 #pragma unroll
