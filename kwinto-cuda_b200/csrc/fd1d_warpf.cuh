@@ -276,8 +276,8 @@ __global__ void __launch_bounds__(128, MINB) fd1d_warpf_kernel(const Fd1dBatch B
                             F aA[8], aB[8], gA[8], gB[8], dA[8], dB[8], pA[8], pB[8];
                             KW_W_LD8(tbase + T_A + CW * cA, aA);
                             KW_W_LD8(tbase + T_A + CW * cB, aB);
-                            tmem::wait_ld_dep(aA);
-                            tmem::wait_ld_dep(aB);
+                            tmem::hot_wait(aA);
+                            tmem::hot_wait(aB);
                             KW_W_LD8(tbase + T_G + CW * cA, gA);
                             KW_W_LD8(tbase + T_G + CW * cB, gB);
                             KW_W_LD8(tbase + T_D + CW * cA, dA);
@@ -292,12 +292,12 @@ __global__ void __launch_bounds__(128, MINB) fd1d_warpf_kernel(const Fd1dBatch B
                                 yA[i] = fma(aA[i], yA[i - 1], vr[8 * cA + i]);
                                 yB[i] = fma(aB[i], yB[i - 1], vr[8 * cB + i]);
                             }
-                            tmem::wait_ld_dep(gA);
-                            tmem::wait_ld_dep(gB);
-                            tmem::wait_ld_dep(dA);
-                            tmem::wait_ld_dep(dB);
-                            tmem::wait_ld_dep(pA);
-                            tmem::wait_ld_dep(pB);
+                            tmem::hot_wait(gA);
+                            tmem::hot_wait(gB);
+                            tmem::hot_wait(dA);
+                            tmem::hot_wait(dB);
+                            tmem::hot_wait(pA);
+                            tmem::hot_wait(pB);
                             F uA = Uin[cA], uB = Uin[cB];
 #pragma unroll
                             for (int i = 7; i >= 0; --i) {
