@@ -478,7 +478,9 @@ __global__ void __launch_bounds__(BS == 1 ? 256 : 128, MINB) fd1d_warp_kernel(co
                 }
                 tmem::wait_ld_dep(an);  // nothing in flight when the arrays are rewritten
             };
-            if constexpr (RT) {
+            // BS = 2: the march as given keeps its level-specialised loops (7 % faster than the run-time form,
+            // variant 235 vs 233); only the European march uses run-time levels -- at most 3 + 1 hot loops per SM
+            if constexpr (RT && BS != 2) {
                 if (euro)
                     march(std::integral_constant<int, 0>{}, std::integral_constant<bool, BS == 1>{});
                 else
