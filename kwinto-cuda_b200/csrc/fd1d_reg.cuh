@@ -190,10 +190,12 @@ __device__ __forceinline__ void setup_lu(const Fd1dBatch& B, const PdeScalars& s
     double* s_ib_first = scr + 6 * P;  // [P]
     double* s_ib_last = scr + 7 * P;   // [P]
     // ---------------- set-up: grid, payoff --------------------------------------------
+    double xl[M];  // this chunk's nodes stay in registers: only the two neighbours come back from shared memory
 #pragma unroll
     for (int i = 0; i < M; ++i) {
         const int j = k * M + i;
         const double x = x_node(sc, B.density, j);
+        xl[i] = x;
         xs[j] = x;
         double p = 0.;
         if (j < xDim) p = payoff_node(sc.put, x);
@@ -206,12 +208,14 @@ __device__ __forceinline__ void setup_lu(const Fd1dBatch& B, const PdeScalars& s
     // ---------------- B rows, Moebius-composed pivots ---------------------------------
     {
         double bl[M], bb[M], bu[M];
+        const double x_before = xs[k > 0 ? k * M - 1 : 0];
+        const double x_after = xs[k < P - 1 ? k * M + M : N - 1];
 #pragma unroll
         for (int i = 0; i < M; ++i) {
             const int j = k * M + i;
-            const double xm = xs[j > 0 ? j - 1 : 0];
-            const double xp = xs[j < N - 1 ? j + 1 : N - 1];
-            b_row(sc, j, xDim, xm, xs[j], xp, bl[i], bb[i], bu[i]);
+            const double xm = i ? xl[i - 1] : x_before;           // = xs[j > 0 ? j - 1 : 0]
+            const double xp = i < M - 1 ? xl[i + 1] : x_after;    // = xs[j < N - 1 ? j + 1 : N - 1]
+            b_row(sc, j, xDim, xm, xl[i], xp, bl[i], bb[i], bu[i]);
         }
         s_bu_last[k] = bu[M - 1];
         __syncthreads();

@@ -39,6 +39,13 @@
 
 namespace kwfd1d {
 
+// Index swizzle of the set-up stage.  The set-up thread of chunk k writes nodes 8k .. 8k+7 and the owning
+// warp's lane l reads nodes 32l .. 32l+31 (NCH = 4), i.e. both sides walk shared memory with a stride of 64 resp.
+// 256 bytes between lanes: 8- and 32-way bank conflicts (the owner's pull was 20 % of the set-up time,
+// profiles/r1_au_*).  XOR-ing the low four bits of the node index with bits of j >> 4 and j >> 5 makes both
+// patterns conflict-free per half-warp; it permutes inside aligned groups of 16 doubles, so arrays stay N long.
+__device__ __forceinline__ int stage_swz(int j) { return j ^ ((j >> 4) & 7) ^ ((j >> 5) & 15); }
+
 template <int NCH, int CTA = 128>
 struct WarpSmem {
     static constexpr int N = 8 * NCH * 32;  // nodes per PDE tile
@@ -152,11 +159,12 @@ __global__ void __launch_bounds__(BS == 1 ? 256 : 128, MINB) fd1d_warp_kernel(co
                 if (lane == 0) scr[k >> 5] = bmax;
 #pragma unroll
                 for (int i = 0; i < M; ++i) {
-                    st[0 * N + k * M + i] = a[i];
-                    st[1 * N + k * M + i] = g[i];
-                    st[2 * N + k * M + i] = D[i];
-                    st[3 * N + k * M + i] = pj[i];
-                    st[4 * N + k * M + i] = v[i];
+                    const int js = stage_swz(k * M + i);
+                    st[0 * N + js] = a[i];
+                    st[1 * N + js] = g[i];
+                    st[2 * N + js] = D[i];
+                    st[3 * N + js] = pj[i];
+                    st[4 * N + js] = v[i];
                 }
                 st_A[k] = Pp[M - 1];
                 st_G[k] = Q0;
@@ -179,12 +187,12 @@ __global__ void __launch_bounds__(BS == 1 ? 256 : 128, MINB) fd1d_warp_kernel(co
 #pragma unroll
                         for (int arr = 0; arr < 4; ++arr) {
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) t8[i] = st[arr * N + ch * 8 + i];
+                            for (int i = 0; i < 8; ++i) t8[i] = st[arr * N + stage_swz(ch * 8 + i)];
                             tmem::st8(tbase + 16 * NCH * arr + 16 * c, t8);
                         }
                     }
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) vr[8 * c + i] = st[4 * N + ch * 8 + i];
+                    for (int i = 0; i < 8; ++i) vr[8 * c + i] = st[4 * N + stage_swz(ch * 8 + i)];
                     Ac[c] = st_A[ch];
                     Gc[c] = st_G[ch];
                     R0c[c] = st_R0[ch];
