@@ -27,6 +27,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "bs":
     sys.exit(0)
 run(1024,12,40,233); run(1024,12,40,241); run(1024,12,24,201); run(1024,12,24,221)
 run(2048,10,24,331); run(4096,8,12,431); run(512,12,40,0); run(1024,12,24,0,"f32"); run(300,12,40,0)
+run(512,12,40,133); run(300,12,40,133); run(1024,12,40,1233,"f32"); run(512,12,40,1133,"f32")
 PY
 for tool in memcheck racecheck; do
   echo "== $tool"; timeout 1200 compute-sanitizer --tool $tool --print-limit 5 python /tmp/san.py ${2:-} 2>&1 | grep -vE "^$" | tail -25
