@@ -703,6 +703,10 @@ int kw_fd1d_create(const kw_fd1d_config* cfg, kw_fd1d_handle** out)
             if (h->var_small) {
                 if (int rc = prepare_variant(h, h->var_small, prop, h->ctas_per_sm_small, h->regs_small)) return rc;
                 h->small_below = (uint32_t)(h->sm_count * h->ctas_per_sm * std::max(1, h->var->pdes_per_cta));
+                // Layout W for x <= 1024 finishes any batch up to one wave in one group period (1.0 ms at 1024^2,
+                // 0.27 ms at 512^2), the CTA-per-PDE kernel needs a second and third round from 444 / 888 PDEs on:
+                // measured crossover at ~0.7 of a wave (profiles/r1_bv_small_batch_crossover.log)
+                if (h->var->pdes_per_cta == 4 && !h->var->wide_nwp) h->small_below = h->small_below * 3 / 4;
             }
         }
         // fused FD1D-BS march: fp64, one Layout W tile of 4 chunks per lane
@@ -792,7 +796,7 @@ int kw_fd1d_price_bs(kw_fd1d_handle* h, const kw_option* assets, size_t n, doubl
         return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::price: FD1D.GPU.BS_FUSED = 2 / 3 needs fp64 and 512 < FD1D.X_GRID_SIZE <= 1024, = 4 fp64 and 256 < FD1D.X_GRID_SIZE <= 1024");
     // auto: fused from one full wave of the persistent grid (4 chains per CTA) upwards; below that the
     // CTA-per-PDE kernel of the two-solve path spreads the batch over more SMs
-    if (h->var_bs && (h->bs_forced || n >= (size_t)h->sm_count * h->ctas_per_sm_bs * 4)) {
+    if (h->var_bs && (h->bs_forced || n >= (size_t)h->sm_count * h->ctas_per_sm_bs * 3)) {  // 3/4 of a wave, as small_below
         // fused: the solve as given (:18) and the solve of the European copies (:21-28) are two value
         // vectors of the same chains marched by one launch; then + (BS - FD_euro) (:30-40)
         if (int rc = price_to_device(h, assets, n, h->d_opts, h->d_prices.p, h->d_prices2.p)) return rc;
