@@ -125,3 +125,34 @@ def test_sharded_gather_world2_gloo(built, tmp_path):
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("ok") == 2
+
+
+def test_stage_swizzle_is_a_conflict_free_permutation():
+    # fd1d_warp.cuh: stage_swz -- the node-index swizzle of the set-up stage (Python copy of the one-line
+    # formula, which is also checked against the source text): a permutation inside aligned groups of 16
+    # doubles, conflict-free per half-warp for the set-up threads' writes (thread k, nodes 8k + i) and for the
+    # owning warp's reads (lane l, nodes 8 * (NCH * l + c) + i)
+    import os
+    import re
+
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "kwinto-cuda_b200", "csrc",
+                            "fd1d_warp.cuh")).read()
+    m = re.search(r"int stage_swz\(int j\) \{ return (.*?); \}", src)
+    assert m and m.group(1) == "j ^ ((j >> 4) & 7) ^ ((j >> 5) & 15)"
+
+    def swz(j):
+        return j ^ ((j >> 4) & 7) ^ ((j >> 5) & 15)
+
+    for n in (512, 1024):
+        assert sorted(swz(j) for j in range(n)) == list(range(n))
+        assert all(swz(j) // 16 == j // 16 for j in range(n))
+    for base in range(0, 128, 16):
+        for i in range(8):
+            banks = [swz(8 * k + i) % 16 for k in range(base, base + 16)]
+            assert len(set(banks)) == 16
+    for nch, worst_allowed in ((4, 1), (2, 2)):
+        for half in (0, 16):
+            for c in range(nch):
+                for i in range(8):
+                    banks = [swz((lane * nch + c) * 8 + i) % 16 for lane in range(half, half + 16)]
+                    assert max(banks.count(b) for b in banks) <= worst_allowed
