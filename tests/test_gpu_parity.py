@@ -388,6 +388,48 @@ def test_baseline_size_config2_sample_and_properties(oracle):
     # idempotence / determinism at full size
     _, again = p.price(o)
     assert np.array_equal(again, got)
+    # homogeneity: price = k * f(log(s / k), chain) (src/Pricer/kwFd1d.cpp:146-157), so scaling spot and
+    # strike by a power of two scales every price exactly
+    h = o.copy()
+    h["s"] *= 4.0
+    h["k"] *= 4.0
+    _, ph = p.price(h)
+    assert np.array_equal(ph, 4.0 * got)
+    # order of the batch is irrelevant, bit for bit
+    perm = np.random.default_rng(2).permutation(n)
+    _, pp = p.price(o[perm])
+    assert np.array_equal(pp, got[perm])
+
+
+@pytest.mark.parametrize("n,x,t,seed,sample", [(1048576, 1024, 1024, 7, 256), (65536, 4096, 4096, 11, 32)])
+def test_baseline_size_configs_4_and_5_properties(n, x, t, seed, sample, oracle):
+    """BASELINE.json configs[3] (1 M options at 1024^2; one GPU prices the whole portfolio here, the sharded
+    run is test_host.py's gloo test and bench.py --gpus N) and configs[4] (65536 options at 4096^2), at full
+    size: an oracle sample plus size-independent properties."""
+    from kwfd1d.synthetic import synthetic_options
+
+    o = synthetic_options(n, seed)
+    p = make_pricer(t, x, **{"FD1D.GPU.COMPRESS": 0})
+    err, got = p.price(o)
+    assert err == "" and got.shape == (n,) and np.all(np.isfinite(got))
+    idx = np.random.default_rng(3).choice(n, sample, replace=False)
+    want, oerr = oracle.fd1d(o[idx], t, x, compress=False)
+    assert oerr == "" and maxdiff(got[idx], want) <= TOL
+    assert np.all(got >= np.maximum(o["k"] - o["s"], 0) - 1e-3) and np.all(got <= o["k"])
+    # a shard priced on its own (what rank g of N does, kwfd1d/sharded.py) = the same options inside the whole
+    # batch, bit for bit: the full-size stand-in for "shard, price, gather"
+    m = n // 8
+    variant = p.info()["variant"]
+    q = make_pricer(t, x, **{"FD1D.GPU.COMPRESS": 0, "FD1D.GPU.VARIANT": variant})
+    for g in (0, 5):
+        _, part = q.price(o[g * m:(g + 1) * m])
+        assert np.array_equal(part, got[g * m:(g + 1) * m])
+    # homogeneity at full size
+    h = o.copy()
+    h["s"] *= 0.5
+    h["k"] *= 0.5
+    _, ph = p.price(h)
+    assert np.array_equal(ph, 0.5 * got)
 
 
 def test_cpp_pricer_interface():
