@@ -19,6 +19,7 @@
 #include "fd1d_reg.cuh"
 #include "fd1d_soa.cuh"
 #include "fd1d_warp.cuh"
+#include "fd1d_iw.cuh"
 #include "fd1d_wide.cuh"
 #include "fd1d_warpf.cuh"
 #include "fd1d_warp_bs.cuh"
@@ -72,6 +73,16 @@ struct RegVariant {
         ID, KW_FD1D_F64, 8, 128, MINB_, false, false, fd1d_warp_kernel<4, MINB_, ICMP_, PAIR_>,    \
             WarpSmem<4>::bytes(), 256, 4                                                           \
     }
+#define KW_VARIANT_WS(ID, NCH_, MINB_)                                                            \
+    {                                                                                              \
+        ID, KW_FD1D_F64, 8, 32 * NCH_, MINB_, false, false, fd1d_warp_kernel<NCH_, MINB_, false, true, 0, false, true>, \
+            WarpSmem<NCH_>::bytes(), 64 * NCH_, 4                                                  \
+    }
+#define KW_VARIANT_IW(ID, NCH_, MINB_)                                                            \
+    {                                                                                              \
+        ID, KW_FD1D_F64, 8, 32 * NCH_, MINB_, false, false, fd1d_iw_kernel<NCH_, MINB_>,           \
+            IwSmem<NCH_>::bytes(), 64 * NCH_, 4                                                    \
+    }
 #define KW_VARIANT_WRT(ID, MINB_)                                                                 \
     {                                                                                              \
         ID, KW_FD1D_F64, 8, 128, MINB_, false, false, fd1d_warp_kernel<4, MINB_, false, true, 0, true>, \
@@ -98,6 +109,12 @@ struct RegVariant {
             4 / NWP_, NWP_, fd1d_wide_setup_kernel<128 * NWP_>, fd1d_wide_kernel<NWP_, 2, ICMP_>,  \
             sizeof(double) * 16 * 128 * NWP_, WideSlot<128 * NWP_>::doubles, ICMP_                 \
     }
+#define KW_VARIANT_WIDES(ID, NWP_)                                                                \
+    {                                                                                              \
+        ID, KW_FD1D_F64, 8, 128 * NWP_, 2, false, false, nullptr, WideSmem<NWP_>::bytes(), 256,    \
+            4 / NWP_, NWP_, fd1d_wide_setup_kernel<128 * NWP_>, fd1d_wide_kernel<NWP_, 2, false, true>, \
+            sizeof(double) * 16 * 128 * NWP_, WideSlot<128 * NWP_>::doubles, false                 \
+    }
 #define KW_VARIANT_F32(ID, M_, P_, MINB_)                                                         \
     {                                                                                              \
         ID, KW_FD1D_F32, M_, P_, MINB_, false, false, fd1d_reg_kernel<float, M_, P_, MINB_, false, false>, \
@@ -112,7 +129,11 @@ const RegVariant g_variants[] = {
     KW_VARIANT(101, 8, 64, 6, false, false),   // x <= 512, CTA per PDE (batches below one wave of Layout W)
     KW_VARIANT(102, 8, 64, 8, true, true),
     KW_VARIANT(103, 8, 64, 6, true, false),
-    KW_VARIANT_W(233, 2, false, true),              // x <= 1024: Layout W (warp per PDE, coefficients in tensor memory), chunk pairs
+    KW_VARIANT_IW(237, 4, 2),                  // x <= 1024: Layout W with independent warps (fd1d_iw.cuh): warp-level set-up, no CTA
+                                               // barrier, PDEs handed out by an atomic counter, rotated split march (23.9 ms)
+    KW_VARIANT_WS(236, 4, 2),                  // Layout W, CTA-cooperative set-up, chunk pairs, every pair phase a basic block of its
+                                               // own, a~ and g~ loaded twice (25.8 vs 27.6 ms for 233)
+    KW_VARIANT_W(233, 2, false, true),         // the round-1 default: the chunk-pair phases of a step in one basic block
     KW_VARIANT(201, 8, 128, 3, false, false),  // x <= 1024, CTA per PDE (batches below one wave of Layout W)
     KW_VARIANT(202, 8, 128, 3, true, false),
     KW_VARIANT(203, 8, 128, 4, true, true),
@@ -125,13 +146,17 @@ const RegVariant g_variants[] = {
     KW_VARIANT_W(232, 2, true, false),
     KW_VARIANT_W(231, 2, false, false),  // one chunk at a time, next chunk's a~ prefetched
     KW_VARIANT_W(234, 2, true, true),
+    KW_VARIANT_IW(137, 2, 2),  // 237's two-chunk twin (7.30 ms at 512^2 against 6.91 for 133)
+    KW_VARIANT_WS(136, 2, 2),  // 133 in the form of 236 (slower on the two-chunk tile: 7.65 vs 6.92 ms at 512^2)
     KW_VARIANT_WRT(235, 2),  // 233 with the scan-level count as a run-time value: one march loop instead of five
     KW_VARIANT_W2(241, 2, false),  // v in tensor memory, floor from shared memory
     KW_VARIANT_W2(242, 2, true),
     KW_VARIANT_WIDE(331, 2, false),            // x <= 2048: Layout W over two warps per PDE
+    KW_VARIANT_WIDES(336, 2),                  // 331 with split chunk-pair phases
     KW_VARIANT(301, 8, 256, 1, false, false),  // x <= 2048, CTA per PDE (small batches)
     KW_VARIANT(302, 8, 256, 2, true, true),
     KW_VARIANT_WIDE(431, 4, false),            // x <= 4096: Layout W over four warps per PDE
+    KW_VARIANT_WIDES(436, 4),                  // 431 with split chunk-pair phases
     KW_VARIANT(401, 8, 512, 1, true, true),    // x <= 4096, CTA per PDE (small batches)
     KW_VARIANT(402, 8, 512, 1, true, false),
     // fp32 march (fp64 set-up): FD1D.GPU.PRECISION = f32
@@ -185,6 +210,7 @@ __global__ void status_reset_kernel(unsigned int* status)
     status[0] = 0u;
     status[1] = 0xffffffffu;
     status[2] = status[3] = status[4] = status[5] = status[6] = status[7] = 0u;
+    status[8] = 0u;  // work counter of the independent-warp kernels
 }
 
 // device-side chain compression of `n` device-resident options; fills the batch's PDE tables
@@ -354,6 +380,9 @@ size_t soa_chunk(const kw_fd1d_handle* h, size_t n_pde)
 // enqueue the solve of `n_pde` PDEs on `st`; all pointers are device pointers
 int launch_batch(kw_fd1d_handle* h, Fd1dBatch B, cudaStream_t st)
 {
+    for (int i = 0; i < 4; ++i) B.opq_lim[i] = INT32_MAX;
+    B.opq_zero = 0;
+    B.work_counter = B.status + 8;
     status_reset_kernel<<<1, 1, 0, st>>>(B.status);
     h->launches += 1;
     h->last_n_pde = B.n_pde;
@@ -520,7 +549,7 @@ int price_to_device(kw_fd1d_handle* h, const kw_option* assets, size_t n, DevBuf
                     double* d_out, double* d_out_eu = nullptr)
 {
     KW_CUDA(h, d_opts.reserve(n));
-    KW_CUDA(h, h->d_status.reserve(8));
+    KW_CUDA(h, h->d_status.reserve(16));
     KW_CUDA(h, cudaMemcpyAsync(d_opts.p, assets, n * sizeof(kw_option), cudaMemcpyHostToDevice, h->stream));
     Fd1dBatch B;
     memset(&B, 0, sizeof B);
@@ -734,7 +763,7 @@ int kw_fd1d_create(const kw_fd1d_config* cfg, kw_fd1d_handle** out)
     KW_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     KW_CUDA(h, cudaEventCreate(&h->ev0));
     KW_CUDA(h, cudaEventCreate(&h->ev1));
-    KW_CUDA(h, h->d_status.reserve(8));
+    KW_CUDA(h, h->d_status.reserve(16));
     KW_CUDA(h, h->h_status.reserve(8));
     return KW_FD1D_OK;
 }

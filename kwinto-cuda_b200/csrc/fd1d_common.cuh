@@ -34,7 +34,7 @@ struct Fd1dBatch {
     const uint32_t* n_pde_dev;  // device-side compression: the PDE count lives in HBM (overrides n_pde)
     double* prices;
     unsigned int* status;  // [0] = number of out-of-range options, [1] = smallest such index,
-                           // [2..6] = PDEs marched in carry mode 0..4 (layout B)
+                           // [2..7] = PDEs marched per carry mode / scan-level count, [8] = work counter (fd1d_iw.cuh)
     uint32_t n_pde;
     uint32_t pde_base;     // first PDE of this launch (layout A chunks the batch)
     int32_t tDim;
@@ -43,6 +43,12 @@ struct Fd1dBatch {
     double density;
     double scale;
     double* prices_eu;     // fused FD1D-BS march only (fd1d_warp_bs.cuh): the European solution's prices
+    // Values the kernels must not be able to fold (fd1d_warp.cuh, SPLIT): opq_lim[] = INT32_MAX ("step < lim" is
+    // always true), opq_zero = 0.  capi.cu: make_batch().
+    int32_t opq_lim[4];
+    uint32_t opq_zero;
+    // fd1d_iw.cuh: the next PDE to hand out (status[8], zeroed by status_reset_kernel before every launch)
+    unsigned int* work_counter;
 };
 
 __device__ __forceinline__ uint32_t batch_n_pde(const Fd1dBatch& B)

@@ -1,0 +1,488 @@
+// fd1d_iw.cuh -- Layout W with INDEPENDENT warps: every warp sets its own PDE up, marches it and prices
+// its chain; the warps of a CTA share nothing but the tensor-memory allocation.
+//
+// Same scheme and algebra as fd1d_warp.cuh (reference src/Math/kwFd1d.cpp:61-136 + src/Math/kwMath.cpp:16-49,
+// hoisted constant-dt LU in pivot-scaled unknowns, true-sweep formulation, chunk pairs, a~ g~ D p in tensor
+// memory, v in registers) and the same arithmetic in the same order -- prices are bit-identical to
+// fd1d_warp_kernel's.  What changes is who does the set-up and when:
+//   * fd1d_warp_kernel sets the four PDEs of a CTA up one after the other with all 128 threads (Layout B's
+//     setup_lu), five __syncthreads per PDE.  That phase is latency-bound (20 % issue utilisation) and while it
+//     runs, only the SM's other CTA marches: measured fixed cost 2.0-2.7 ms of a 25.8 ms launch.
+//   * here a lane owns its 8*NCH contiguous nodes from the first instruction on: x grid, payoff, rows of
+//     B = 1 - dt/2 A, the Moebius-composed pivots (the lane's chunk maps -> one warp scan -> the reference's pivot
+//     recurrence inside every chunk), a~, g~, D.  The rows are parked in the tensor-memory columns that will hold
+//     a~, g~, D.  No shared-memory stage, no CTA barrier.  A warp in set-up issues little, so the sub-partition's
+//     other warp marches at a lone warp's rate meanwhile; PDEs are handed out by an atomic counter, so there
+//     is no wave tail either.
+//   * the x grid is not kept: the scan-level test and the epilogue's interpolation recompute x_j with the
+//     function the set-up used (same bits).
+#pragma once
+#include <type_traits>
+
+#include "fd1d_reg.cuh"
+#include "tmem.cuh"
+
+namespace kwfd1d {
+
+// out-of-line copies of the transcendental-heavy helpers: the set-up calls them from rolled loops
+__device__ __noinline__ double x_node_ni(const PdeScalars& s, double density, int j) { return x_node(s, density, j); }
+__device__ __noinline__ double payoff_node_ni(bool put, double x) { return payoff_node(put, x); }
+
+template <int NCH>
+struct IwSmem {
+    static constexpr int N = 8 * NCH * 32;  // nodes per PDE tile
+    static constexpr int SCR = 28 * 32;     // set-up scratch per warp: chunk maps [16][32], chunk scalars [12][32]
+    // doubles per warp: final v of its PDE [N] (the payoff stage during set-up) | set-up scratch [SCR]
+    static constexpr size_t bytes() { return sizeof(double) * (size_t)(4 * (N + SCR)); }
+};
+
+template <int NCH, int MINB>
+__global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
+{
+    static_assert(NCH == 4 || NCH == 2, "4 chunks per lane (512 < x <= 1024) or 2 (256 < x <= 512)");
+    constexpr int N = IwSmem<NCH>::N;
+    constexpr int NODES = 8 * NCH;  // per lane
+
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    double* vfin = smem + warp * (N + IwSmem<NCH>::SCR);
+    double* scr = vfin + N;
+    const int xDim = B.xDim;
+    const int nsteps = B.tDim - 1;
+
+    // tensor memory: 4 arrays x 8*NCH doubles per lane = 64*NCH columns per warp
+    __shared__ uint32_t s_taddr;
+    if (threadIdx.x < 32) tmem::alloc<64 * NCH>(smem_addr(&s_taddr));
+    tmem::fence_before();
+    __syncthreads();
+    tmem::fence_after();
+    const uint32_t tbase = s_taddr + ((uint32_t)(warp & 3) << 21);
+    const uint32_t tbase2 = tbase + B.opq_zero;  // the same address, opaque to the compiler (fd1d_warp.cuh, SPLIT)
+    constexpr uint32_t T_A = 0, T_G = 16 * NCH, T_D = 32 * NCH, T_P = 48 * NCH;  // column offsets, 16 per chunk
+
+    const uint32_t n_pde = batch_n_pde(B);
+    for (;;) {
+        uint32_t my_pde = 0;
+        if (lane == 0) my_pde = atomicAdd(B.work_counter, 1u);
+        my_pde = __shfl_sync(FULL, my_pde, 0);
+        if (my_pde >= n_pde) break;
+
+        const uint32_t rep = B.pde_rep ? __ldg(B.pde_rep + my_pde) : my_pde;
+        const kw_option opt = load_option(B.opts + rep);
+        const PdeScalars sc = pde_scalars(opt, B);
+
+        double vr[NODES];
+        double Ac[NCH], Gc[NCH], R0c[NCH];
+        double bmax = 0.;
+        // ================= set-up (setup_lu of fd1d_reg.cuh, one warp, NCH chunks per lane) ==============
+        // Rolled over the lane's chunks (the code runs once per PDE next to seven marching warps: a fully unrolled
+        // set-up is 13 k instructions and evicts their hot loops from the instruction cache).  What crosses a chunk
+        // boundary travels in a loop-carried scalar, in tensor memory (the rows of B, then 1/beta in the diagonal's
+        // columns) or in the warp's shared scratch ([index][lane], conflict-free).
+        {
+            const int j0 = lane * NODES;
+            double* s_v = vfin;            // [NODES][32] payoff, until the registers take it
+            double* s_m = scr;             // [4 * NCH][32] chunk maps
+            double* s_k = scr + 16 * 32;   // [3 * NCH][32] chunk scalars
+            // ---- grid, payoff, projection floor, rows of B (parked in tensor memory)
+            double bu_carry = 0.;
+            {
+                double x_m1 = lane ? x_node_ni(sc, B.density, j0 - 1) : 0.;
+                double x_0 = x_node_ni(sc, B.density, j0);
+                if (lane == 0) x_m1 = x_0;
+#pragma unroll 1
+                for (int c = 0; c < NCH; ++c) {
+                    double xl[10];  // nodes 8c - 1 .. 8c + 8 of this lane
+                    xl[0] = x_m1;
+                    xl[1] = x_0;
+#pragma unroll
+                    for (int i = 1; i <= 8; ++i) xl[1 + i] = x_node_ni(sc, B.density, j0 + 8 * c + i);
+                    if (lane == 31 && c == NCH - 1) xl[9] = xl[8];  // past the tile: the last node again
+                    double t8[8], bl[8], bb[8], bu[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int j = j0 + 8 * c + i;
+                        double p = 0.;
+                        if (j < xDim) p = payoff_node_ni(sc.put, xl[1 + i]);
+                        s_v[(8 * c + i) * 32 + lane] = p;
+                        // projection skips the last node (src/Math/kwFd1d.cpp:130); European: never
+                        t8[i] = (sc.american && j < xDim - 1) ? p : -CUDART_INF;
+                        b_row(sc, j, xDim, xl[i], xl[1 + i], xl[2 + i], bl[i], bb[i], bu[i]);
+                    }
+                    tmem::st8(tbase + T_P + 16 * c, t8);
+                    tmem::st8(tbase + T_A + 16 * c, bl);
+                    tmem::st8(tbase + T_G + 16 * c, bb);
+                    tmem::st8(tbase + T_D + 16 * c, bu);
+                    bu_carry = bu[7];
+                    x_m1 = xl[8];
+                    x_0 = xl[9];
+                }
+                tmem::wait_st();
+            }
+            double bu_prev_lane = __shfl_up_sync(FULL, bu_carry, 1);
+            if (lane == 0) bu_prev_lane = 0.;
+            // ---- pivots: beta_j = b_j - c_j / beta_{j-1}, c_j = bl_j bu_{j-1}, as the Moebius map
+            //      [[b_j, -c_j], [1, 0]] on (num; den); compose per chunk, per lane, scan over the lanes
+            {
+                Mat2 Lm = {1., 0., 0., 1.};
+                bu_carry = bu_prev_lane;
+#pragma unroll 1
+                for (int c = 0; c < NCH; ++c) {
+                    double bl[8], bb[8], bu[8];
+                    tmem::ld8(tbase + T_A + 16 * c, bl);
+                    tmem::ld8(tbase + T_G + 16 * c, bb);
+                    tmem::ld8(tbase + T_D + 16 * c, bu);
+                    tmem::wait_ld_dep(bl, bb, bu);
+                    Mat2 m = {1., 0., 0., 1.};
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const double cc = bl[i] * (i ? bu[i > 0 ? i - 1 : 0] : bu_carry);
+                        Mat2 n;
+                        n.m00 = fma(bb[i], m.m00, -cc * m.m10);
+                        n.m01 = fma(bb[i], m.m01, -cc * m.m11);
+                        n.m10 = m.m00;
+                        n.m11 = m.m01;
+                        m = n;
+                        if ((i & 3) == 3) mat_normalise(m);
+                    }
+                    bu_carry = bu[7];
+                    s_m[(4 * c + 0) * 32 + lane] = m.m00;
+                    s_m[(4 * c + 1) * 32 + lane] = m.m01;
+                    s_m[(4 * c + 2) * 32 + lane] = m.m10;
+                    s_m[(4 * c + 3) * 32 + lane] = m.m11;
+                    Lm = mat_mul(m, Lm);
+                    mat_normalise(Lm);
+                }
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const Mat2 o = mat_shfl_up(Lm, d);
+                    if (lane >= d) {
+                        Lm = mat_mul(Lm, o);
+                        mat_normalise(Lm);
+                    }
+                }
+                const Mat2 E = mat_shfl_up(Lm, 1);
+                double num = lane ? E.m00 : 1.;
+                double den = lane ? E.m10 : 0.;
+                // ---- pivots inside every chunk, in the reference's order (src/Math/kwMath.cpp:32-33):
+                //      gam = au[j-1] / bet;  bet = a[j] - al[j] * gam;  1/beta replaces the diagonal in tensor memory
+                bu_carry = bu_prev_lane;
+#pragma unroll 1
+                for (int c = 0; c < NCH; ++c) {
+                    double prev = den == 0. ? CUDART_INF : num / den;  // the pivot just before the chunk
+                    {
+                        const double m00 = s_m[(4 * c + 0) * 32 + lane], m01 = s_m[(4 * c + 1) * 32 + lane];
+                        const double m10 = s_m[(4 * c + 2) * 32 + lane], m11 = s_m[(4 * c + 3) * 32 + lane];
+                        const double nn = fma(m00, num, m01 * den);
+                        const double dd = fma(m10, num, m11 * den);
+                        const double sn = 1. / fmax(fabs(nn), fabs(dd));
+                        num = nn * sn;
+                        den = dd * sn;
+                    }
+                    double bl[8], bb[8], bu[8];
+                    tmem::ld8(tbase + T_A + 16 * c, bl);
+                    tmem::ld8(tbase + T_G + 16 * c, bb);
+                    tmem::ld8(tbase + T_D + 16 * c, bu);
+                    tmem::wait_ld_dep(bl, bb, bu);
+                    double ib[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const double gam = (i ? bu[i > 0 ? i - 1 : 0] : bu_carry) / prev;
+                        const double beta = __dsub_rn(bb[i], __dmul_rn(bl[i], gam));
+                        ib[i] = 1. / beta;
+                        prev = beta;
+                    }
+                    bu_carry = bu[7];
+                    tmem::st8(tbase + T_G + 16 * c, ib);
+                }
+                tmem::wait_st();
+            }
+            // ---- a~, g~, D into tensor memory (over the rows), chunk scalars
+            {
+                double ib[8];
+                tmem::ld8(tbase + T_G, ib);
+                tmem::wait_ld_dep(ib);
+                double ib_last_lane, ib_first_lane = ib[0];
+                {
+                    double t[8];
+                    tmem::ld8(tbase + T_G + 16 * (NCH - 1), t);
+                    tmem::wait_ld_dep(t);
+                    ib_last_lane = t[7];
+                }
+                double ib_prev = __shfl_up_sync(FULL, ib_last_lane, 1);    // 1/beta of the node before the chunk
+                double ib_next_lane = __shfl_down_sync(FULL, ib_first_lane, 1);
+                if (lane == 0) ib_prev = 0.;
+                if (lane == 31) ib_next_lane = 0.;
+#pragma unroll 1
+                for (int c = 0; c < NCH; ++c) {
+                    double bl[8], bu[8], ibn[8];
+                    tmem::ld8(tbase + T_A + 16 * c, bl);
+                    tmem::ld8(tbase + T_D + 16 * c, bu);
+                    tmem::ld8(tbase + T_G + 16 * (c < NCH - 1 ? c + 1 : c), ibn);  // the next chunk's 1/beta
+                    tmem::wait_ld_dep(bl, bu, ibn);
+                    const double ib_next = c < NCH - 1 ? ibn[0] : ib_next_lane;
+                    double a[8], g[8], D[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int j = j0 + 8 * c + i;
+                        a[i] = -bl[i] * (i ? ib[i > 0 ? i - 1 : 0] : ib_prev);
+                        g[i] = -bu[i] * (i < 7 ? ib[i < 7 ? i + 1 : i] : ib_next);
+                        D[i] = j < xDim ? 2. * ib[i] : 0.;
+                    }
+                    tmem::st8(tbase + T_A + 16 * c, a);
+                    tmem::st8(tbase + T_G + 16 * c, g);
+                    tmem::st8(tbase + T_D + 16 * c, D);
+                    // chunk scalars: A = prod a~, G = prod g~, R0 = d(u~_first)/d(Yin) (backward sweep of the prefix products)
+                    double Pp[8];
+                    Pp[0] = a[0];
+#pragma unroll
+                    for (int i = 1; i < 8; ++i) Pp[i] = a[i] * Pp[i - 1];
+                    double Q0 = g[7], R0 = Pp[7];
+#pragma unroll
+                    for (int i = 6; i >= 0; --i) {
+                        Q0 = g[i] * Q0;
+                        R0 = fma(g[i], R0, Pp[i]);
+                    }
+                    s_k[(3 * c + 0) * 32 + lane] = Pp[7];
+                    s_k[(3 * c + 1) * 32 + lane] = Q0;
+                    s_k[(3 * c + 2) * 32 + lane] = R0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) bmax = fmax(bmax, D[i] != 0. ? fabs(2. / D[i]) : 1.);
+                    ib_prev = ib[7];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) ib[i] = ibn[i];
+                }
+                tmem::wait_st();
+            }
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) bmax = fmax(bmax, __shfl_xor_sync(FULL, bmax, d));
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                Ac[c] = s_k[(3 * c + 0) * 32 + lane];
+                Gc[c] = s_k[(3 * c + 1) * 32 + lane];
+                R0c[c] = s_k[(3 * c + 2) * 32 + lane];
+            }
+#pragma unroll
+            for (int i = 0; i < NODES; ++i) vr[i] = s_v[i * 32 + lane];
+            __syncwarp();  // the scratch is the final-v stage later
+        }
+
+        // ================= cross-lane scan multipliers (lane aggregates) ================================
+        double AfL[5], GbL[5];
+        {
+            double AL = Ac[0], GL = Gc[0];
+#pragma unroll
+            for (int c = 1; c < NCH; ++c) {
+                AL *= Ac[c];
+                GL *= Gc[c];
+            }
+            double A = AL;
+#pragma unroll
+            for (int d = 0; d < 5; ++d) {
+                const int s = 1 << d;
+                const double o = __shfl_up_sync(FULL, A, s);
+                AfL[d] = lane >= s ? A : 0.;
+                if (lane >= s) A *= o;
+            }
+            double G = GL;
+#pragma unroll
+            for (int d = 0; d < 5; ++d) {
+                const int s = 1 << d;
+                const double o = __shfl_down_sync(FULL, G, s);
+                GbL[d] = lane < 32 - s ? G : 0.;
+                if (lane < 32 - s) G *= o;
+            }
+        }
+        // keep the multipliers as values: the compiler would otherwise re-derive the first levels from Ac[] / Gc[]
+        // inside the march loop (6 DMUL + the lane predicate per step) to save two registers
+#pragma unroll
+        for (int d = 0; d < 5; ++d) asm volatile("" : "+d"(AfL[d]), "+d"(GbL[d]));
+        // ================= how many levels carry anything (DESIGN.md "Truncation") =======================
+        int levels = 0;
+        {
+            const double tol = 0x1p-56 / (bmax * (double)B.tDim);
+            const double x_here = fmax(0., x_node(sc, B.density, min(lane * NODES, xDim - 1)));
+#pragma unroll
+            for (int d = 0; d < 5; ++d) {
+                const int src = min((lane + (1 << d)) * NODES + NODES - 1, xDim - 1);
+                const double growth = sc.put ? 1. : exp(fmax(0., x_node(sc, B.density, src)) - x_here);
+                const bool bad = !(fabs(AfL[d]) <= tol) || !(fabs(GbL[d]) * growth <= tol);
+                if (__any_sync(FULL, bad)) levels = d + 1;
+            }
+            if (B.max_mode <= 1) levels = 5;  // FD1D.GPU.EXACT >= 1: every level
+            if (levels < 1) levels = 1;
+        }
+
+        // ================= time march: fd1d_warp_kernel's SPLIT chunk-pair form ==========================
+        auto march = [&](auto lev_c) {
+            constexpr int LEV = decltype(lev_c)::value;
+            double e[NCH], f[NCH];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                double a8[8], g8[8];
+                tmem::ld8(tbase + T_A + 16 * c, a8);
+                tmem::ld8(tbase + T_G + 16 * c, g8);
+                tmem::wait_ld_dep(a8, g8);
+                double y[8];
+                y[0] = vr[8 * c];
+#pragma unroll
+                for (int i = 1; i < 8; ++i) y[i] = fma(a8[i], y[i - 1], vr[8 * c + i]);
+                e[c] = y[7];
+                double u = y[7];
+#pragma unroll
+                for (int i = 6; i >= 0; --i) u = fma(g8[i], u, y[i]);
+                f[c] = u;
+            }
+            double Yin[NCH], Uin[NCH];
+            // ---- the scans of one step: lane aggregates, Kogge-Stone over the lanes, chunk-entry / -exit values
+            auto scan = [&]() {
+                double S = e[0];
+#pragma unroll
+                for (int c = 1; c < NCH; ++c) S = fma(Ac[c], S, e[c]);
+#pragma unroll
+                for (int d = 0; d < LEV; ++d) {
+                    const double o = __shfl_up_sync(FULL, S, 1 << d);
+                    S = fma(AfL[d], o, S);
+                }
+                {
+                    const double o = __shfl_up_sync(FULL, S, 1);
+                    Yin[0] = lane ? o : 0.;
+                }
+#pragma unroll
+                for (int c = 1; c < NCH; ++c) Yin[c] = fma(Ac[c - 1], Yin[c - 1], e[c - 1]);
+                // backward: chunk-start values with the true forward carry, scan, chunk-exit values
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) f[c] = fma(R0c[c], Yin[c], f[c]);
+                double T = f[NCH - 1];
+#pragma unroll
+                for (int c = NCH - 2; c >= 0; --c) T = fma(Gc[c], T, f[c]);
+#pragma unroll
+                for (int d = 0; d < LEV; ++d) {
+                    const double o = __shfl_down_sync(FULL, T, 1 << d);
+                    T = fma(GbL[d], o, T);
+                }
+                {
+                    const double o = __shfl_down_sync(FULL, T, 1);
+                    Uin[NCH - 1] = lane < 31 ? o : 0.;
+                }
+#pragma unroll
+                for (int c = NCH - 2; c >= 0; --c) Uin[c] = fma(Gc[c + 1], Uin[c + 1], f[c + 1]);
+            };
+            // ---- true forward sweeps of the chunk pair (cA, cA + 1) from Yin
+            auto fwd_pair = [&](int cA, double (&yA)[8], double (&yB)[8]) {
+                const int cB = cA + 1;
+                double aA[8], aB[8];
+                tmem::ld8(tbase + T_A + 16 * cA, aA);
+                tmem::ld8(tbase + T_A + 16 * cB, aB);
+                tmem::hot_wait(aA, aB);
+                yA[0] = fma(aA[0], Yin[cA], vr[8 * cA]);
+                yB[0] = fma(aB[0], Yin[cB], vr[8 * cB]);
+#pragma unroll
+                for (int i = 1; i < 8; ++i) {
+                    yA[i] = fma(aA[i], yA[i - 1], vr[8 * cA + i]);
+                    yB[i] = fma(aB[i], yB[i - 1], vr[8 * cB + i]);
+                }
+            };
+            // ---- true backward sweeps from Uin, projection, next step's local sweeps (a~, g~ loaded again)
+            auto back_pair = [&](int cA, double (&yA)[8], double (&yB)[8]) {
+                const int cB = cA + 1;
+                double gA[8], gB[8], dA[8], dB[8], pA[8], pB[8];
+                tmem::ld8(tbase + T_G + 16 * cA, gA);
+                tmem::ld8(tbase + T_G + 16 * cB, gB);
+                tmem::ld8(tbase + T_D + 16 * cA, dA);
+                tmem::ld8(tbase + T_D + 16 * cB, dB);
+                tmem::ld8(tbase + T_P + 16 * cA, pA);
+                tmem::ld8(tbase + T_P + 16 * cB, pB);
+                tmem::hot_wait(gA, gB, dA);
+                tmem::hot_wait(dB, pA, pB);
+                double uA = Uin[cA], uB = Uin[cB];
+#pragma unroll
+                for (int i = 7; i >= 0; --i) {
+                    uA = fma(gA[i], uA, yA[i]);
+                    uB = fma(gB[i], uB, yB[i]);
+                    const double rA = fma(dA[i], uA, -vr[8 * cA + i]);
+                    const double rB = fma(dB[i], uB, -vr[8 * cB + i]);
+                    vr[8 * cA + i] = max_like_std(rA, pA[i]);
+                    vr[8 * cB + i] = max_like_std(rB, pB[i]);
+                }
+                double aA[8], aB[8];
+                tmem::ld8(tbase2 + T_A + 16 * cA, aA);
+                tmem::ld8(tbase2 + T_A + 16 * cB, aB);
+                tmem::ld8(tbase2 + T_G + 16 * cA, gA);
+                tmem::ld8(tbase2 + T_G + 16 * cB, gB);
+                tmem::hot_wait(aA, aB);
+                tmem::hot_wait(gA, gB);
+                yA[0] = vr[8 * cA];
+                yB[0] = vr[8 * cB];
+#pragma unroll
+                for (int i = 1; i < 8; ++i) {
+                    yA[i] = fma(aA[i], yA[i - 1], vr[8 * cA + i]);
+                    yB[i] = fma(aB[i], yB[i - 1], vr[8 * cB + i]);
+                }
+                e[cA] = yA[7];
+                e[cB] = yB[7];
+                uA = yA[7];
+                uB = yB[7];
+#pragma unroll
+                for (int i = 6; i >= 0; --i) {
+                    uA = fma(gA[i], uA, yA[i]);
+                    uB = fma(gB[i], uB, yB[i]);
+                }
+                f[cA] = uA;
+                f[cB] = uB;
+            };
+            // Rotated loop.  Block X: pair 0 backwards (its forward sweeps were done at the end of the previous
+            // iteration).  Block Z: the other pair in full, then the NEXT step's scans with pair 0's forward sweeps
+            // behind them -- the shuffles' latency hides behind the sweeps of the same basic block.
+            double y0A[8], y0B[8];
+            scan();
+            fwd_pair(0, y0A, y0B);
+            for (int step = 0; step < nsteps; ++step) {
+                if (step < B.opq_lim[0]) back_pair(0, y0A, y0B);  // always true: basic-block boundary
+                if (step < B.opq_lim[1]) {
+#pragma unroll
+                    for (int h = 2; h < NCH; h += 2) {
+                        double yA[8], yB[8];
+                        fwd_pair(h, yA, yB);
+                        back_pair(h, yA, yB);
+                    }
+                    scan();
+                    fwd_pair(0, y0A, y0B);  // after the last step: computed and dropped
+                }
+            }
+            tmem::wait_ld();  // nothing in flight when the arrays are rewritten
+        };
+        switch (levels) {
+            case 1: march(std::integral_constant<int, 1>{}); break;
+            case 2: march(std::integral_constant<int, 2>{}); break;
+            case 3: march(std::integral_constant<int, 3>{}); break;
+            case 4: march(std::integral_constant<int, 4>{}); break;
+            default: march(std::integral_constant<int, 5>{}); break;
+        }
+        if (lane == 0) {
+            // histogram buckets shared with Layout B: 0 = exact requested, 1 = all 5 levels, 2/3/4 = 4/3/2, 5 = 1 level
+            const int bucket = B.max_mode == 0 ? 0 : (levels == 5 ? 1 : 6 - levels);
+            atomicAdd(&B.status[2 + bucket], 1u);
+        }
+        // ================= epilogue: interpolate every option of this chain ===============================
+#pragma unroll
+        for (int i = 0; i < NODES; ++i) vfin[lane * NODES + i] = vr[i];
+        __syncwarp();
+        {
+            uint32_t q0, q1;
+            chain_range(B, my_pde, q0, q1);
+            for (uint32_t q = q0 + lane; q < q1; q += 32) {
+                const uint32_t oi = B.csr_opt ? __ldg(B.csr_opt + q) : q;
+                price_option(B, oi, [&](int j) { return x_node(sc, B.density, j); }, [&](int j) { return vfin[j]; });
+            }
+        }
+        __syncwarp();  // vfin is rewritten by the next PDE
+    }
+    tmem::fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem::dealloc<64 * NCH>(s_taddr);
+}
+
+}  // namespace kwfd1d

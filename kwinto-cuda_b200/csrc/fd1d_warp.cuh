@@ -76,9 +76,16 @@ struct WarpSmem {
 // copies of it.  Warps of an SM then execute the same code whatever their PDE's level count: the SM's
 // instruction cache holds ~32 KB, a specialised step is 7 KB, and with BS there are two roles as well
 // (ncu stall_no_instruction 0.92 cycles per instruction with 6 hot loops per SM, profiles/r1_aw_*).
-template <int NCH, int MINB, bool ICMP, bool PAIR = false, int BS = 0, bool RT = false>
+// SPLIT: every chunk-pair phase of a step is a basic block of its own (an always-true branch on a launch
+// parameter ptxas cannot see through, Fd1dBatch::opq_lim) and a~, g~ are loaded a second time for the next step's
+// local sweeps (through Fd1dBatch::opq_zero, so that the second tcgen05.ld is not merged with the first).  ptxas
+// schedules inside basic blocks: without the split it hoists the tcgen05.ld of all four chunks to the top of the
+// step, runs out of 16-register destination blocks and copies the survivors out (118 moves of 417 instructions);
+// with it a value dies where it is used (8 moves of 342 instructions, no spills).
+template <int NCH, int MINB, bool ICMP, bool PAIR = false, int BS = 0, bool RT = false, bool SPLIT = false>
 __global__ void __launch_bounds__(BS == 1 ? 256 : 128, MINB) fd1d_warp_kernel(const Fd1dBatch B)
 {
+    static_assert(!SPLIT || PAIR, "SPLIT is a form of the chunk-pair phase");
     static_assert(NCH == 4 || (NCH == 2 && PAIR), "4 chunks per lane (512 < x <= 1024) or 2 (256 < x <= 512)");
     static_assert(!BS || (PAIR && !ICMP && RT), "fused FD1D-BS march: chunk pairs, run-time scan levels");
     static_assert(BS != 1 || NCH == 4, "BS = 1 (European copy in warp w + 4): 512 < x <= 1024 only");
@@ -117,6 +124,7 @@ __global__ void __launch_bounds__(BS == 1 ? 256 : 128, MINB) fd1d_warp_kernel(co
     __syncthreads();
     tmem::fence_after();
     const uint32_t tbase = s_taddr + ((uint32_t)(warp & 3) << 21);
+    const uint32_t tbase2 = SPLIT ? tbase + B.opq_zero : tbase;  // the same address, opaque to the compiler
     constexpr uint32_t T_A = 0, T_G = 16 * NCH, T_D = 32 * NCH, T_P = 48 * NCH;  // column offsets, 16 per chunk
 
     const uint32_t n_pde = batch_n_pde(B);
@@ -390,6 +398,7 @@ __global__ void __launch_bounds__(BS == 1 ? 256 : 128, MINB) fd1d_warp_kernel(co
                     if constexpr (PAIR) {
 #pragma unroll
                         for (int h = 0; h < NCH; h += 2) {
+                            if (SPLIT && !(step < B.opq_lim[h >> 1])) continue;  // never taken: basic-block boundary
                             const int cA = h, cB = h + 1;
                             double aA[8], aB[8], gA[8], gB[8], dA[8], dB[8], pA[8], pB[8];
                             KW_W_LD8(tbase + T_A + 16 * cA, aA);
@@ -434,6 +443,14 @@ __global__ void __launch_bounds__(BS == 1 ? 256 : 128, MINB) fd1d_warp_kernel(co
                                 }
                             }
                             // next step's local sweeps of both chunks, interleaved
+                            if constexpr (SPLIT) {
+                                KW_W_LD8(tbase2 + T_A + 16 * cA, aA);
+                                KW_W_LD8(tbase2 + T_A + 16 * cB, aB);
+                                KW_W_LD8(tbase2 + T_G + 16 * cA, gA);
+                                KW_W_LD8(tbase2 + T_G + 16 * cB, gB);
+                                tmem::hot_wait(aA, aB);
+                                tmem::hot_wait(gA, gB);
+                            }
                             yA[0] = vr[8 * cA];
                             yB[0] = vr[8 * cB];
 #pragma unroll

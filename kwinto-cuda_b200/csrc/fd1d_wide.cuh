@@ -114,7 +114,8 @@ __device__ __forceinline__ void group_barrier(int grp)
         asm volatile("bar.sync 2, %0;" ::"n"(NTHREADS) : "memory");
 }
 
-template <int NWP, int MINB, bool ICMP>
+// SPLIT: as in fd1d_warp.cuh -- every chunk-pair phase a basic block of its own, a~ and g~ loaded twice.
+template <int NWP, int MINB, bool ICMP, bool SPLIT = false>
 __global__ void __launch_bounds__(128, MINB) fd1d_wide_kernel(const Fd1dBatch B, const double* __restrict__ ws,
                                                                uint32_t pde_base, uint32_t count)
 {
@@ -151,6 +152,7 @@ __global__ void __launch_bounds__(128, MINB) fd1d_wide_kernel(const Fd1dBatch B,
     __syncthreads();
     tmem::fence_after();
     const uint32_t tbase = s_taddr + ((uint32_t)(warp & 3) << 21);
+    const uint32_t tbase2 = SPLIT ? tbase + B.opq_zero : tbase;
     constexpr uint32_t T_A = 0, T_G = 64, T_D = 128, T_P = 192;
 
     const uint32_t n_pde = batch_n_pde(B);
@@ -357,6 +359,7 @@ __global__ void __launch_bounds__(128, MINB) fd1d_wide_kernel(const Fd1dBatch B,
                     // ---- chunk pairs: true sweeps, projection, next step's local sweeps
 #pragma unroll
                     for (int h = 0; h < NCH; h += 2) {
+                        if (SPLIT && !(step < B.opq_lim[h >> 1])) continue;  // never taken: basic-block boundary
                         const int cA = h, cB = h + 1;
                         double aA[8], aB[8], gA[8], gB[8], dA[8], dB[8], pA[8], pB[8];
                         tmem::ld8(tbase + T_A + 16 * cA, aA);
@@ -392,6 +395,14 @@ __global__ void __launch_bounds__(128, MINB) fd1d_wide_kernel(const Fd1dBatch B,
                             const double rB = fma(dB[i], uB, -vr[8 * cB + i]);
                             vr[8 * cA + i] = ICMP ? max_like_icmp(rA, pA[i]) : max_like_std(rA, pA[i]);
                             vr[8 * cB + i] = ICMP ? max_like_icmp(rB, pB[i]) : max_like_std(rB, pB[i]);
+                        }
+                        if constexpr (SPLIT) {
+                            tmem::ld8(tbase2 + T_A + 16 * cA, aA);
+                            tmem::ld8(tbase2 + T_A + 16 * cB, aB);
+                            tmem::ld8(tbase2 + T_G + 16 * cA, gA);
+                            tmem::ld8(tbase2 + T_G + 16 * cB, gB);
+                            tmem::wait_ld_dep(aA, aB);
+                            tmem::wait_ld_dep(gA, gB);
                         }
                         yA[0] = vr[8 * cA];
                         yB[0] = vr[8 * cB];

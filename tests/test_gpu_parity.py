@@ -164,7 +164,7 @@ def test_layouts_agree_with_reference(layout):
         assert maxdiff(got, g[k + "/fd1d"]) <= TOL, (layout, k)
 
 
-@pytest.mark.parametrize("variant", [201, 202, 203, 204, 205, 211, 213, 221, 222, 231, 232, 233, 234, 235, 241, 242])
+@pytest.mark.parametrize("variant", [201, 202, 203, 204, 205, 211, 213, 221, 222, 231, 232, 233, 234, 235, 236, 237, 241, 242])
 def test_all_1024_variants(variant):
     g, _ = synthetic_cases()
     p = make_pricer(1024, 1024, **{"FD1D.GPU.VARIANT": variant})
@@ -173,8 +173,8 @@ def test_all_1024_variants(variant):
     assert err == "" and maxdiff(got, g["mix_1024/fd1d"]) <= TOL
 
 
-@pytest.mark.parametrize("variant,x", [(1, 256), (2, 256), (101, 512), (102, 512), (103, 512), (133, 512), (133, 300), (301, 2048),
-                                        (302, 2048), (401, 4096), (402, 4096), (331, 2048), (331, 1100), (431, 4096), (431, 3000)])
+@pytest.mark.parametrize("variant,x", [(1, 256), (2, 256), (101, 512), (102, 512), (103, 512), (133, 512), (133, 300), (136, 512), (136, 300), (137, 512), (137, 300), (237, 1024), (237, 700), (301, 2048),
+                                        (302, 2048), (401, 4096), (402, 4096), (331, 2048), (331, 1100), (431, 4096), (431, 3000), (336, 2048), (336, 1100), (436, 4096), (436, 3000)])
 def test_other_variants(variant, x, oracle):
     from kwfd1d.synthetic import synthetic_options
 
@@ -216,7 +216,7 @@ def test_device_side_compression_matches_host_side():
     assert err == "" and np.array_equal(pa, pb)
 
 
-@pytest.mark.parametrize("variant", [221, 222, 231, 232, 233, 234, 241, 242])
+@pytest.mark.parametrize("variant", [221, 222, 231, 232, 233, 234, 236, 241, 242])
 def test_tmem_variants_all_modes_and_reuse(variant, oracle):
     """Tensor-memory variants: every carry mode (forced through FD1D.GPU.EXACT), more PDEs than resident
     CTAs (the TMEM arrays are rewritten per PDE), mixed calls/puts/Europeans, non-multiple-of-8 grid."""
@@ -326,7 +326,7 @@ def test_edges_and_errors(oracle):
     assert kwfd1d.PricerFactory.create(cfg)[0].startswith("PricerFactory: Fd1dGpu_Pricer::init")
 
 
-@pytest.mark.parametrize("x,t,n,variants", [(1024, 48, 1500, (233,)), (2048, 32, 800, (331,)), (4096, 24, 400, (431,))])
+@pytest.mark.parametrize("x,t,n,variants", [(1024, 48, 1500, (233, 236, 237)), (2048, 32, 800, (331, 336)), (4096, 24, 400, (431, 436))])
 def test_range_error_in_warp_layouts(x, t, n, variants, oracle):
     """The reference's out-of-range error (src/Math/kwFd1d.cpp:151-153) through the warp-per-PDE kernels:
     batches big enough for the auto dispatch to take Layout W / wide Layout W, one bad option in the middle."""
