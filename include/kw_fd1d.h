@@ -87,7 +87,11 @@ typedef struct kw_fd1d_config {
                          /* as the reference.  1: always two solves.  4: variant 253 for every batch size.   */
                          /* Measured experiments with the same prices: 3 = the two marches side  */
                          /* by side in warps w and w + 4 (variant 252), 2 = both in one warp's step (251)    */
-    int32_t reserved;
+    int32_t n_devices;   /* FD1D.GPU.DEVICES: 0 / 1 = one device (`device`); N > 1 = the devices `device` ... `device` + N - 1;   */
+                         /* -1 = every visible device from `device` on.  With more than one device the handle owns one  */
+                         /* complete per-device context (stream, device buffers, pinned staging) per GPU and            */
+                         /* kw_fd1d_price / kw_fd1d_price_bs split the batch into contiguous blocks, price them          */
+                         /* concurrently and land every block's prices in the caller's array (kw_fd1d_create_multi)      */
 } kw_fd1d_config;
 
 typedef struct kw_fd1d_handle kw_fd1d_handle;
@@ -110,12 +114,22 @@ typedef struct kw_fd1d_info {
     uint64_t last_n_pde;      /* PDEs solved by the last price call                          */
     uint32_t mode_count[6];   /* layout B: PDEs of the last SYNCHRONISED call per carry mode 0..4 */
     char device_name[128];
+    int32_t n_devices;        /* devices the handle owns (1 for a single-device handle)      */
+    int32_t devices_used;     /* devices the last price call spread the batch over            */
+    double last_wall_ms;      /* multi-device: host wall time of the last price call (last_kernel_ms = max over devices) */
 } kw_fd1d_info;
 
 void kw_fd1d_config_default(kw_fd1d_config* cfg);
 
 /* Fd1d_Pricer::init (reference src/Pricer/kwFd1d.cpp:9-19) + device set-up. */
 int kw_fd1d_create(const kw_fd1d_config* cfg, kw_fd1d_handle** out);
+/* The same for an explicit list of device ordinals (cfg.device / cfg.n_devices are ignored; an ordinal may repeat:
+ * two shards on one GPU share it through two streams).  The reference prices a portfolio with ONE call,
+ * Portfolio::price -> Pricer::price (reference src/Utils/kwPortfolio.cpp:87-98): with this handle that one call
+ * uses every listed GPU -- contiguous blocks of the batch, one host thread, stream and buffer set per device, no
+ * device-to-device traffic (a PDE never reads another PDE's data, reference src/Math/kwFd1d.cpp:61-136); the
+ * "gather" is each device's D2H into its slice of `prices`.  kw_fd1d_price_device needs a single-device handle. */
+int kw_fd1d_create_multi(const kw_fd1d_config* cfg, const int32_t* devices, int32_t n_devices, kw_fd1d_handle** out);
 void kw_fd1d_destroy(kw_fd1d_handle* h);
 
 /* Fd1d_Pricer::price (reference src/Pricer/kwFd1d.cpp:21-160).  HOST buffers: `assets` has n
@@ -183,6 +197,11 @@ int kw_fd1d_tmem_probe(int32_t device, double* out16);
  * DFMAs all read three registers, so this -- not the one-register figure of kw_fd1d_fp64_peak -- is its
  * practical ceiling.  out[10]. */
 int kw_fd1d_dfma_probe(int32_t device, double* out10);
+
+/* 1 if this build of the library carries kernel variant `id` for `precision` (cfg.variant), else 0.  The default
+ * build ships the variants the dispatch table can reach; the other variants measured in DESIGN.md are compiled
+ * with -DKW_EXPERIMENTS (make -C kwinto-cuda_b200/csrc EXPERIMENTS=1). */
+int kw_fd1d_has_variant(int32_t id, int32_t precision);
 
 const char* kw_fd1d_version(void);
 

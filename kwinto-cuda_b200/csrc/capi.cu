@@ -10,8 +10,10 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -22,7 +24,9 @@
 #include "fd1d_iw.cuh"
 #include "fd1d_wide.cuh"
 #include "fd1d_warpf.cuh"
+#ifdef KW_EXPERIMENTS
 #include "fd1d_warp_bs.cuh"
+#endif
 #include "compress.cuh"
 #include "microbench.cuh"
 
@@ -121,20 +125,34 @@ struct RegVariant {
             RegSmem<M_, P_>::bytes(false, false)                                                   \
     }
 
-// the first entry of each P is the default of the per-xDim dispatch
+// The first entry of each P is the default of the per-xDim dispatch.  The shipped library carries the
+// kernels the dispatch can reach; every other variant measured along the way (DESIGN.md "Tried") is compiled only
+// with -DKW_EXPERIMENTS (make EXPERIMENTS=1), so that they cost no build time, binary size or test matrix by default.
 const RegVariant g_variants[] = {
     KW_VARIANT(1, 8, 32, 12, false, false),    // x <= 256
-    KW_VARIANT(2, 8, 32, 16, true, true),
     KW_VARIANT_WN(133, 2, 2),                  // x <= 512: Layout W with 2 chunks per lane (one chunk pair)
     KW_VARIANT(101, 8, 64, 6, false, false),   // x <= 512, CTA per PDE (batches below one wave of Layout W)
-    KW_VARIANT(102, 8, 64, 8, true, true),
-    KW_VARIANT(103, 8, 64, 6, true, false),
     KW_VARIANT_IW(237, 4, 2),                  // x <= 1024: Layout W with independent warps (fd1d_iw.cuh): warp-level set-up, no CTA
                                                // barrier, PDEs handed out by an atomic counter, rotated split march (23.9 ms)
+    KW_VARIANT(201, 8, 128, 3, false, false),  // x <= 1024, CTA per PDE (batches below one wave of Layout W)
+    KW_VARIANT_WIDE(331, 2, false),            // x <= 2048: Layout W over two warps per PDE
+    KW_VARIANT(301, 8, 256, 1, false, false),  // x <= 2048, CTA per PDE (small batches)
+    KW_VARIANT_WIDES(436, 4),                  // x <= 4096: Layout W over four warps per PDE, split chunk-pair phases (34.8 vs 36.0 ms)
+    KW_VARIANT(401, 8, 512, 1, true, true),    // x <= 4096, CTA per PDE (small batches)
+    // fp32 march (fp64 set-up): FD1D.GPU.PRECISION = f32
+    KW_VARIANT_F32(1001, 8, 32, 16),
+    KW_VARIANT_F32(1101, 8, 64, 8),
+    KW_VARIANT_WF(1233, 4, 2),   // Layout W, float march, 512 < x <= 1024
+    KW_VARIANT_F32(1201, 8, 128, 4),
+    KW_VARIANT_F32(1301, 8, 256, 2),
+    KW_VARIANT_F32(1401, 8, 512, 1),
+#ifdef KW_EXPERIMENTS
+    KW_VARIANT(2, 8, 32, 16, true, true),
+    KW_VARIANT(102, 8, 64, 8, true, true),
+    KW_VARIANT(103, 8, 64, 6, true, false),
     KW_VARIANT_WS(236, 4, 2),                  // Layout W, CTA-cooperative set-up, chunk pairs, every pair phase a basic block of its
                                                // own, a~ and g~ loaded twice (25.8 vs 27.6 ms for 233)
     KW_VARIANT_W(233, 2, false, true),         // the round-1 default: the chunk-pair phases of a step in one basic block
-    KW_VARIANT(201, 8, 128, 3, false, false),  // x <= 1024, CTA per PDE (batches below one wave of Layout W)
     KW_VARIANT(202, 8, 128, 3, true, false),
     KW_VARIANT(203, 8, 128, 4, true, true),
     KW_VARIANT(204, 8, 128, 4, true, false),
@@ -151,36 +169,28 @@ const RegVariant g_variants[] = {
     KW_VARIANT_WRT(235, 2),  // 233 with the scan-level count as a run-time value: one march loop instead of five
     KW_VARIANT_W2(241, 2, false),  // v in tensor memory, floor from shared memory
     KW_VARIANT_W2(242, 2, true),
-    KW_VARIANT_WIDE(331, 2, false),            // x <= 2048: Layout W over two warps per PDE
-    KW_VARIANT_WIDES(336, 2),                  // 331 with split chunk-pair phases
-    KW_VARIANT(301, 8, 256, 1, false, false),  // x <= 2048, CTA per PDE (small batches)
+    KW_VARIANT_WIDES(336, 2),                  // 331 with split chunk-pair phases (18.3 vs 17.7 ms)
     KW_VARIANT(302, 8, 256, 2, true, true),
-    KW_VARIANT_WIDE(431, 4, false),            // x <= 4096: Layout W over four warps per PDE
-    KW_VARIANT_WIDES(436, 4),                  // 431 with split chunk-pair phases
-    KW_VARIANT(401, 8, 512, 1, true, true),    // x <= 4096, CTA per PDE (small batches)
+    KW_VARIANT_WIDE(431, 4, false),            // the round-1 four-warp kernel
     KW_VARIANT(402, 8, 512, 1, true, false),
-    // fp32 march (fp64 set-up): FD1D.GPU.PRECISION = f32
-    KW_VARIANT_F32(1001, 8, 32, 16),
-    KW_VARIANT_F32(1101, 8, 64, 8),
     KW_VARIANT_WF(1133, 2, 2),   // Layout W, float march, 256 < x <= 512 (slower than 1101: 6.0 M vs 7.1 M options/s)
-    KW_VARIANT_WF(1233, 4, 2),   // Layout W, float march, 512 < x <= 1024
-    KW_VARIANT_F32(1201, 8, 128, 4),
-    KW_VARIANT_F32(1301, 8, 256, 2),
-    KW_VARIANT_F32(1401, 8, 512, 1),
+#endif
 };
 // fused FD1D-BS marches (one set-up and one tensor-memory copy of a~, g~, D for the solve as given and the
-// solve of the European copy).  253 (default where it applies; fd1d_warp.cuh, BS = 2): every warp marches its
-// chain as given, then the European copy.  252 (FD1D.GPU.BS_FUSED = 3; BS = 1): eight warps per CTA, warp w
-// marches PDE w as given while warp w + 4 marches the European copy.  251 (FD1D.GPU.BS_FUSED = 2;
+// solve of the European copy).  253 / 153 (default where they apply; fd1d_warp.cuh, BS = 2): every warp marches its
+// chain as given, then the European copy.  Experiments: 252 (FD1D.GPU.BS_FUSED = 3; BS = 1): eight warps per CTA,
+// warp w marches PDE w as given while warp w + 4 marches the European copy; 251 (FD1D.GPU.BS_FUSED = 2;
 // fd1d_warp_bs.cuh): both solutions in one warp's step (instruction-cache bound, slower than two solves).
-const RegVariant g_bs_variant = {252, KW_FD1D_F64, 8, 256, 1, false, false, fd1d_warp_kernel<4, 1, false, true, 1, true>,
-                                 WarpSmem<4, 256>::bytes(), 256, 4};
 const RegVariant g_bs2_variant = {253, KW_FD1D_F64, 8, 128, 2, false, false, fd1d_warp_kernel<4, 2, false, true, 2, true>,
                                   WarpSmem<4>::bytes(), 256, 4};
 const RegVariant g_bs2n2_variant = {153, KW_FD1D_F64, 8, 64, 2, false, false, fd1d_warp_kernel<2, 2, false, true, 2, true>,
                                     WarpSmem<2>::bytes(), 128, 4};  // 256 < x <= 512, two chunks per lane
+#ifdef KW_EXPERIMENTS
+const RegVariant g_bs_variant = {252, KW_FD1D_F64, 8, 256, 1, false, false, fd1d_warp_kernel<4, 1, false, true, 1, true>,
+                                 WarpSmem<4, 256>::bytes(), 256, 4};
 const RegVariant g_bs1_variant = {251, KW_FD1D_F64, 8, 128, 2, false, false, fd1d_warp_bs_kernel<2>,
                                   Warp2Smem<4>::bytes(), 256, 4};
+#endif
 constexpr int kNumVariants = sizeof(g_variants) / sizeof(g_variants[0]);
 constexpr int kMaxRegX = 4096;
 
@@ -349,6 +359,13 @@ struct kw_fd1d_handle {
     DevBuf<double> d_soa;
     PinBuf<uint32_t> h_idx;  // rep | start | csr staging
     PinBuf<unsigned int> h_status;
+
+    // Multi-device handle (kw_fd1d_create_multi / cfg.n_devices > 1): this object only coordinates; every entry
+    // of `shards` is a complete single-device handle (its own stream, device buffers, pinned staging) and prices a
+    // contiguous block of the batch on its device.  Empty for a single-device handle.
+    std::vector<kw_fd1d_handle*> shards;
+    uint32_t shards_used = 0;  // shards the last call spread the batch over
+    double last_wall_ms = 0.;  // multi-device: wall time of the last price call (max over shards is in last_kernel_ms)
 };
 
 namespace {
@@ -509,8 +526,11 @@ int compress(kw_fd1d_handle* h, const kw_option* a, size_t n, size_t& m, uint32_
 
 int compress_on_device(kw_fd1d_handle* h, Fd1dBatch& B, const kw_option* d_opts, size_t n, cudaStream_t st)
 {
-    uint32_t cap = 64;
-    while (cap < 2 * n) cap <<= 1;
+    uint64_t cap64 = 64;
+    while (cap64 < 2 * (uint64_t)n) cap64 <<= 1;
+    if (cap64 > (1ull << 31))
+        return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::price: batch too large for device-side chain compression (FD1D.GPU.COMPRESS = 1 takes up to 2^30 options)");
+    const uint32_t cap = (uint32_t)cap64;
     // slab: slot_rep, slot_cnt, slot_pde [cap] | opt_slot, rep, seg_start, seg_cnt, seg_fill, members [n] | counters [2]
     KW_CUDA(h, h->d_chain.reserve(3 * (size_t)cap + 6 * n + 2));
     ChainTable T;
@@ -682,10 +702,48 @@ void kw_fd1d_config_default(kw_fd1d_config* cfg)
     cfg->exact = 0;
 }
 
+int kw_fd1d_create_multi(const kw_fd1d_config* cfg, const int32_t* devices, int32_t n_devices, kw_fd1d_handle** out)
+{
+    if (!cfg || !out) return KW_FD1D_EINVAL;
+    *out = nullptr;
+    kw_fd1d_handle* h = new kw_fd1d_handle();
+    h->cfg = *cfg;
+    *out = h;
+    if (!devices || n_devices < 1 || n_devices > 64)
+        return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::init: FD1D.GPU.DEVICES needs 1 ... 64 device ordinals");
+    for (int32_t g = 0; g < n_devices; ++g) {
+        kw_fd1d_config c = *cfg;
+        c.device = devices[g];
+        c.n_devices = 1;
+        kw_fd1d_handle* sh = nullptr;
+        const int rc = kw_fd1d_create(&c, &sh);
+        if (rc != KW_FD1D_OK) {
+            const std::string msg = sh ? sh->err : std::string("Fd1dGpu_Pricer::init: out of memory");
+            if (sh) kw_fd1d_destroy(sh);
+            return fail(h, rc, msg + " (device " + std::to_string(devices[g]) + ")");
+        }
+        h->shards.push_back(sh);
+    }
+    h->cfg.device = devices[0];
+    h->cfg.n_devices = n_devices;
+    return KW_FD1D_OK;
+}
+
 int kw_fd1d_create(const kw_fd1d_config* cfg, kw_fd1d_handle** out)
 {
     if (!cfg || !out) return KW_FD1D_EINVAL;
     *out = nullptr;
+    if (cfg->n_devices > 1 || cfg->n_devices < 0) {
+        // cfg.n_devices = N: devices cfg.device ... cfg.device + N - 1; -1: every visible device from cfg.device on
+        int ndev = 0;
+        int32_t want = cfg->n_devices;
+        if (cudaGetDeviceCount(&ndev) == cudaSuccess && want < 0) want = std::max(1, ndev - cfg->device);
+        if (want > 1 || cfg->n_devices > 1) {
+            std::vector<int32_t> devs;
+            for (int32_t g = 0; g < std::max(want, 1); ++g) devs.push_back(cfg->device + g);
+            return kw_fd1d_create_multi(cfg, devs.data(), (int32_t)devs.size(), out);
+        }
+    }
     kw_fd1d_handle* h = new kw_fd1d_handle();
     h->cfg = *cfg;
     *out = h;  // returned even on failure so the caller can read the message; destroy it either way
@@ -744,8 +802,15 @@ int kw_fd1d_create(const kw_fd1d_config* cfg, kw_fd1d_handle** out)
         const bool seq = cfg->bs_fused == 0 || cfg->bs_fused == 4;  // variant 253 / 153
         if (cfg->bs_fused != 1 && cfg->precision == KW_FD1D_F64 && (tile4 || (tile2 && seq)) &&
             (cfg->variant == 0 || cfg->bs_fused >= 2)) {
+#ifdef KW_EXPERIMENTS
             h->var_bs = cfg->bs_fused == 2 ? &g_bs1_variant
                                            : (cfg->bs_fused == 3 ? &g_bs_variant : (tile4 ? &g_bs2_variant : &g_bs2n2_variant));
+#else
+            if (cfg->bs_fused == 2 || cfg->bs_fused == 3)
+                return fail(h, KW_FD1D_EINVAL,
+                            "Fd1dGpu_Pricer::init: FD1D.GPU.BS_FUSED = 2 / 3 are experiments (build with -DKW_EXPERIMENTS)");
+            h->var_bs = tile4 ? &g_bs2_variant : &g_bs2n2_variant;
+#endif
             h->bs_forced = cfg->bs_fused >= 2;
             if (int rc = prepare_variant(h, h->var_bs, prop, h->ctas_per_sm_bs, h->regs_bs)) return rc;
         }
@@ -771,6 +836,8 @@ int kw_fd1d_create(const kw_fd1d_config* cfg, kw_fd1d_handle** out)
 void kw_fd1d_destroy(kw_fd1d_handle* h)
 {
     if (!h) return;
+    for (kw_fd1d_handle* sh : h->shards) kw_fd1d_destroy(sh);
+    h->shards.clear();
     if (h->stream) {
         cudaSetDevice(h->cfg.device);
         cudaStreamSynchronize(h->stream);
@@ -794,8 +861,56 @@ void kw_fd1d_destroy(kw_fd1d_handle* h)
     delete h;
 }
 
+// Multi-device price call: contiguous blocks of the batch, one per device, every device driven by its own host
+// thread through its single-device shard handle (H2D of the block, chain compression, march, D2H of the block's
+// prices straight into the caller's array).  No device-to-device traffic: a PDE never reads another PDE's data
+// (reference src/Math/kwFd1d.cpp:61-136), so the only "gather" is that every shard writes its slice of `prices`.
+// Small batches use fewer devices: every device in use gets at least two waves of its persistent grid, so the
+// kernel each block runs is the one the whole batch would run on one device (bit-identical prices).
+static int price_multi(kw_fd1d_handle* h, const kw_option* assets, size_t n, double* prices, bool bs)
+{
+    h->err.clear();
+    h->launches = 0;
+    if (n == 0) return KW_FD1D_OK;
+    if (!assets || !prices) return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::price: null buffer");
+    if (n > 0xfffffff0ull) return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::price: batch too large");
+    const kw_fd1d_handle* s0 = h->shards[0];
+    const size_t wave = (size_t)std::max(1, s0->sm_count) * std::max(1, s0->ctas_per_sm) *
+                        (s0->var ? std::max(1, s0->var->pdes_per_cta) : 1);
+    size_t use = std::min<size_t>(h->shards.size(), std::max<size_t>(1, n / (2 * wave)));
+    if (h->cfg.variant != 0) use = std::min(h->shards.size(), n);  // pinned kernel: any split gives the same bits
+    h->shards_used = (uint32_t)use;
+    std::vector<int> rc(use, KW_FD1D_OK);
+    auto run = [&](size_t g) {
+        const size_t lo = n * g / use, hi = n * (g + 1) / use;
+        kw_fd1d_handle* sh = h->shards[g];
+        rc[g] = bs ? kw_fd1d_price_bs(sh, assets + lo, hi - lo, prices + lo) : kw_fd1d_price(sh, assets + lo, hi - lo, prices + lo);
+    };
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> th;
+    for (size_t g = 1; g < use; ++g) th.emplace_back(run, g);
+    run(0);
+    for (auto& t : th) t.join();
+    h->last_wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    h->last_n_pde = 0;
+    for (size_t g = 0; g < use; ++g) {
+        h->launches += h->shards[g]->launches;
+        h->last_n_pde += h->shards[g]->last_n_pde;
+    }
+    for (int i = 0; i < 6; ++i) {
+        h->mode_count[i] = 0;
+        for (size_t g = 0; g < use; ++g) h->mode_count[i] += h->shards[g]->mode_count[i];
+    }
+    // the reference reports the FIRST failing option (src/Pricer/kwFd1d.cpp:154-155): blocks are contiguous and in
+    // order, so that is the error of the lowest shard that has one
+    for (size_t g = 0; g < use; ++g)
+        if (rc[g] != KW_FD1D_OK) return fail(h, rc[g], h->shards[g]->err);
+    return KW_FD1D_OK;
+}
+
 int kw_fd1d_price(kw_fd1d_handle* h, const kw_option* assets, size_t n, double* prices)
 {
+    if (h && !h->shards.empty()) return price_multi(h, assets, n, prices, false);
     if (h) h->launches = 0;
     if (!h) return KW_FD1D_EINVAL;
     if (!h->stream) return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::price: pricer was not initialised");
@@ -812,12 +927,14 @@ int kw_fd1d_price(kw_fd1d_handle* h, const kw_option* assets, size_t n, double* 
 
 int kw_fd1d_price_bs(kw_fd1d_handle* h, const kw_option* assets, size_t n, double* prices)
 {
+    if (h && !h->shards.empty()) return price_multi(h, assets, n, prices, true);
     if (h) h->launches = 0;
     if (!h) return KW_FD1D_EINVAL;
     if (!h->stream) return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::price: pricer was not initialised");
     h->err.clear();
     if (n == 0) return KW_FD1D_OK;
     if (!assets || !prices) return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::price: null buffer");
+    if (n > 0xfffffff0ull) return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::price: batch too large");
     KW_CUDA(h, cudaSetDevice(h->cfg.device));
     KW_CUDA(h, h->d_prices.reserve(n));
     KW_CUDA(h, h->d_prices2.reserve(n));
@@ -837,7 +954,16 @@ int kw_fd1d_price_bs(kw_fd1d_handle* h, const kw_option* assets, size_t n, doubl
     }
     // 1. FD as given (src/Pricer/kwFd1d_BlackScholes.cpp:18)
     if (int rc = price_to_device(h, assets, n, h->d_opts, h->d_prices.p)) return rc;
-    if (int rc = check_status(h, h->stream, assets)) return rc;
+    if (int rc = check_status(h, h->stream, assets)) {
+        // the header's promise: the other prices are still written (the failing ones as NaN)
+        if (rc == KW_FD1D_ERANGE) {
+            const std::string msg = h->err;
+            cudaMemcpyAsync(prices, h->d_prices.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+            cudaStreamSynchronize(h->stream);
+            h->err = msg;
+        }
+        return rc;
+    }
     // 2. FD on European copies (:21-28)
     std::vector<kw_option> euro(assets, assets + n);
     for (auto& o : euro) o.e = 0;
@@ -854,6 +980,10 @@ int kw_fd1d_price_device(kw_fd1d_handle* h, const kw_option* d_assets, size_t n,
 {
     if (h) h->launches = 0;
     if (!h) return KW_FD1D_EINVAL;
+    if (!h->shards.empty())
+        return fail(h, KW_FD1D_EINVAL,
+                    "Fd1dGpu_Pricer::price: device-resident buffers live on one device; use a single-device handle per GPU");
+    if (n > 0xfffffff0ull) return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::price: batch too large");
     if (!h->stream) return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::price: pricer was not initialised");
     h->err.clear();
     if (n == 0) return KW_FD1D_OK;
@@ -879,6 +1009,7 @@ int kw_fd1d_price_device(kw_fd1d_handle* h, const kw_option* d_assets, size_t n,
 int kw_fd1d_sync(kw_fd1d_handle* h, void* stream)
 {
     if (!h) return KW_FD1D_EINVAL;
+    if (!h->shards.empty()) return KW_FD1D_OK;  // multi-device price calls return synchronised
     if (!h->stream) return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer: pricer was not initialised");
     KW_CUDA(h, cudaSetDevice(h->cfg.device));
     return check_status(h, (cudaStream_t)stream, nullptr);
@@ -915,7 +1046,25 @@ int kw_fd1d_get_info(const kw_fd1d_handle* hc, kw_fd1d_info* info)
 {
     if (!hc || !info) return KW_FD1D_EINVAL;
     kw_fd1d_handle* h = const_cast<kw_fd1d_handle*>(hc);
+    if (!h->shards.empty()) {
+        // multi-device: the first shard's kernel facts, totals over the shards the last call used
+        if (int rc = kw_fd1d_get_info(h->shards[0], info)) return rc;
+        const uint32_t used = std::max<uint32_t>(1, h->shards_used);
+        for (uint32_t g = 1; g < used; ++g) {
+            kw_fd1d_info gi;
+            if (kw_fd1d_get_info(h->shards[g], &gi) == KW_FD1D_OK) info->last_kernel_ms = std::max(info->last_kernel_ms, gi.last_kernel_ms);
+        }
+        info->launches = h->launches;
+        info->last_n_pde = h->last_n_pde;
+        for (int i = 0; i < 6; ++i) info->mode_count[i] = h->mode_count[i];
+        info->n_devices = (int32_t)h->shards.size();
+        info->devices_used = (int32_t)used;
+        info->last_wall_ms = h->last_wall_ms;
+        return KW_FD1D_OK;
+    }
     memset(info, 0, sizeof *info);
+    info->n_devices = 1;
+    info->devices_used = 1;
     info->device = h->cfg.device;
     info->sm_count = h->sm_count;
     info->layout = h->layout;
@@ -1091,6 +1240,21 @@ int kw_fd1d_dfma_probe(int32_t device, double* out8)
     return KW_FD1D_OK;
 }
 
-const char* kw_fd1d_version(void) { return "kwinto-b200 fd1d 0.1 (sm_100a)"; }
+int kw_fd1d_has_variant(int32_t id, int32_t precision)
+{
+    for (int i = 0; i < kNumVariants; ++i)
+        if (g_variants[i].id == id && g_variants[i].prec == precision) return 1;
+    if (precision == KW_FD1D_F64 && (id == g_bs2_variant.id || id == g_bs2n2_variant.id)) return 1;
+#ifdef KW_EXPERIMENTS
+    if (precision == KW_FD1D_F64 && (id == g_bs_variant.id || id == g_bs1_variant.id)) return 1;
+#endif
+    return 0;
+}
+
+#ifdef KW_EXPERIMENTS
+const char* kw_fd1d_version(void) { return "kwinto-b200 fd1d 0.2 (sm_100a, +experiments)"; }
+#else
+const char* kw_fd1d_version(void) { return "kwinto-b200 fd1d 0.2 (sm_100a)"; }
+#endif
 
 }  // extern "C"

@@ -40,6 +40,9 @@ public:
         c.variant = (int32_t)config.get("FD1D.GPU.VARIANT", 0);
         c.exact = (int32_t)config.get("FD1D.GPU.EXACT", 0);
         c.bs_fused = (int32_t)config.get("FD1D.GPU.BS_FUSED", 0);
+        // FD1D.GPU.DEVICES = N: ONE price() call spreads the portfolio over the devices DEVICE ... DEVICE + N - 1
+        // (-1: every visible device) -- the handle owns a stream, buffers and pinned staging per device
+        c.n_devices = (int32_t)config.get("FD1D.GPU.DEVICES", 0);
         const std::string layout = config.get("FD1D.GPU.LAYOUT", "auto");
         if (layout == "auto")
             c.layout = KW_FD1D_LAYOUT_AUTO;

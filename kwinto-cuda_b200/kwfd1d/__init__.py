@@ -35,7 +35,7 @@ class _CConfig(C.Structure):  # struct kw_fd1d_config
     _fields_ = [("density", C.c_double), ("scale", C.c_double), ("t_grid_size", C.c_int64),
                 ("x_grid_size", C.c_int64), ("device", C.c_int32), ("precision", C.c_int32),
                 ("layout", C.c_int32), ("compress", C.c_int32), ("variant", C.c_int32),
-                ("exact", C.c_int32), ("bs_fused", C.c_int32), ("reserved", C.c_int32)]
+                ("exact", C.c_int32), ("bs_fused", C.c_int32), ("n_devices", C.c_int32)]
 
 
 class _CInfo(C.Structure):  # struct kw_fd1d_info
@@ -43,7 +43,8 @@ class _CInfo(C.Structure):  # struct kw_fd1d_info
                 ("threads_per_pde", C.c_int32), ("nodes_per_thread", C.c_int32), ("ctas_per_sm", C.c_int32),
                 ("regs_per_thread", C.c_int32), ("smem_per_cta", C.c_int32), ("grid", C.c_int32),
                 ("sm_clock_khz", C.c_int32), ("launches", C.c_int32), ("last_kernel_ms", C.c_double),
-                ("last_n_pde", C.c_uint64), ("mode_count", C.c_uint32 * 6), ("device_name", C.c_char * 128)]
+                ("last_n_pde", C.c_uint64), ("mode_count", C.c_uint32 * 6), ("device_name", C.c_char * 128),
+                ("n_devices", C.c_int32), ("devices_used", C.c_int32), ("last_wall_ms", C.c_double)]
 
 
 _lib = None
@@ -63,6 +64,10 @@ def load_library(path: str = LIB_PATH):
     L.kw_fd1d_config_default.restype = None
     L.kw_fd1d_create.argtypes = [C.POINTER(_CConfig), C.POINTER(H)]
     L.kw_fd1d_create.restype = C.c_int
+    L.kw_fd1d_create_multi.argtypes = [C.POINTER(_CConfig), C.POINTER(C.c_int32), C.c_int32, C.POINTER(H)]
+    L.kw_fd1d_create_multi.restype = C.c_int
+    L.kw_fd1d_has_variant.argtypes = [C.c_int32, C.c_int32]
+    L.kw_fd1d_has_variant.restype = C.c_int
     L.kw_fd1d_destroy.argtypes = [H]
     L.kw_fd1d_destroy.restype = None
     L.kw_fd1d_price.argtypes = [H, C.c_void_p, C.c_size_t, C.c_void_p]
@@ -91,9 +96,9 @@ def load_library(path: str = LIB_PATH):
 
 
 EXPORTED_SYMBOLS = [  # every entry point include/kw_fd1d.h declares
-    "kw_fd1d_config_default", "kw_fd1d_create", "kw_fd1d_destroy", "kw_fd1d_price", "kw_fd1d_price_device",
+    "kw_fd1d_config_default", "kw_fd1d_create", "kw_fd1d_create_multi", "kw_fd1d_destroy", "kw_fd1d_price", "kw_fd1d_price_device",
     "kw_fd1d_sync", "kw_fd1d_price_bs", "kw_fd1d_device_count", "kw_fd1d_get_device_props", "kw_fd1d_last_error", "kw_fd1d_get_info", "kw_fd1d_fp64_peak",
-    "kw_fd1d_microbench", "kw_fd1d_tmem_probe", "kw_fd1d_dfma_probe", "kw_fd1d_version",
+    "kw_fd1d_microbench", "kw_fd1d_tmem_probe", "kw_fd1d_dfma_probe", "kw_fd1d_has_variant", "kw_fd1d_version",
 ]
 
 
@@ -149,7 +154,7 @@ class Fd1dGpu_Pricer(Pricer):
     Keys (init): FD1D.DENSITY, FD1D.SCALE, FD1D.T_GRID_SIZE, FD1D.X_GRID_SIZE exactly as the
     reference (src/Pricer/kwFd1d.cpp:12-16) plus FD1D.GPU.DEVICE (int), FD1D.GPU.LAYOUT
     ("auto"|"reg"|"soa"), FD1D.GPU.PRECISION ("f64"), FD1D.GPU.COMPRESS (int 0/1),
-    FD1D.GPU.VARIANT (int), FD1D.GPU.EXACT (int 0/1/2: 0 lets provably negligible carry terms be
+    FD1D.GPU.DEVICES (int N or "0,1,..": one price() call over several GPUs), FD1D.GPU.VARIANT (int), FD1D.GPU.EXACT (int 0/1/2: 0 lets provably negligible carry terms be
     dropped, 2 keeps every term), FD1D.GPU.BS_FUSED (int, "FD1D-BS-GPU" only: 0 = fused
     American + European march (variant 253) for batches of a device wave or more, 1 = always two solves as
     the reference does, 4 = variant 253 for every batch size, 3 / 2 = the measured experiments 252 / 251)."""
@@ -182,8 +187,20 @@ class Fd1dGpu_Pricer(Pricer):
         c.variant = config.get("FD1D.GPU.VARIANT", 0)
         c.exact = config.get("FD1D.GPU.EXACT", 0)
         c.bs_fused = config.get("FD1D.GPU.BS_FUSED", 0)
+        # FD1D.GPU.DEVICES: an int N (devices DEVICE ... DEVICE + N - 1; -1 = all visible) or a comma-separated list
+        # of ordinals ("0,1,2,3"; an ordinal may repeat): ONE price() call then uses all of them (kw_fd1d_create_multi)
+        dev_list = config.get("FD1D.GPU.DEVICES", "")
+        c.n_devices = config.get("FD1D.GPU.DEVICES", 0)
         h = C.c_void_p()
-        rc = self._lib.kw_fd1d_create(C.byref(c), C.byref(h))
+        if dev_list:
+            try:
+                devs = [int(d) for d in str(dev_list).split(",")]
+            except ValueError:
+                return f"Fd1dGpu_Pricer::init: FD1D.GPU.DEVICES = {dev_list} is not a list of device ordinals"
+            arr = (C.c_int32 * len(devs))(*devs)
+            rc = self._lib.kw_fd1d_create_multi(C.byref(c), arr, len(devs), C.byref(h))
+        else:
+            rc = self._lib.kw_fd1d_create(C.byref(c), C.byref(h))
         if rc != KW_FD1D_OK:
             msg = self._lib.kw_fd1d_last_error(h).decode() if h else "Fd1dGpu_Pricer::init: failed"
             if h:
@@ -264,6 +281,12 @@ class PricerFactory:
         if err:
             return "PricerFactory: " + err, None
         return "", pricer
+
+
+def has_variant(variant: int, precision: str = "f64") -> bool:
+    """True if this build of the library carries kernel variant `variant` (experiments need make EXPERIMENTS=1)."""
+    L = load_library()
+    return bool(L.kw_fd1d_has_variant(int(variant), PRECISIONS.get(precision, 0)))
 
 
 def fp64_peak(device: int = 0) -> Tuple[float, float]:

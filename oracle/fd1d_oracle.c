@@ -79,6 +79,28 @@ void kwo_t_grid(double tMax, int64_t tDim, double* t)
         t[j] = tMin + j * dt;
 }
 
+/* TEST HOOK (off by default; with 0 the restatement is bit-for-bit the reference): model "the same reference
+ * built against another libm".  sinh() and exp() are not correctly rounded in any libm -- glibc's are < 1 ulp,
+ * CUDA's <= 2 ulp -- so two faithful implementations of src/Pricer/kwFd1d.cpp:120-139 legitimately differ in the
+ * last bits of x_j and of the payoff.  With a jitter of n, every sinh() / exp() result is moved by 0..n ulp in a
+ * pseudo-random direction.  tests/ use the resulting price change as the measured libm sensitivity of a grid
+ * shape: where it exceeds 1e-9 (few time steps on a very fine grid, dt/dx^2 in the thousands) the reference does
+ * not define its own prices to 1e-9 and the GPU-vs-oracle bar is that sensitivity (DESIGN.md "Parity budget"). */
+static int g_libm_jitter = 0;
+void kwo_set_libm_jitter(int ulps) { g_libm_jitter = ulps; }
+static double libm_jitter(double v, uint64_t key)
+{
+    if (!g_libm_jitter) return v;
+    key += 0x9e3779b97f4a7c15ull;
+    key = (key ^ (key >> 30)) * 0xbf58476d1ce4e5b9ull;
+    key = (key ^ (key >> 27)) * 0x94d049bb133111ebull;
+    key ^= key >> 31;
+    const int steps = (int)(key % (uint64_t)(g_libm_jitter + 1));
+    const double to = (key >> 40) & 1 ? INFINITY : -INFINITY;
+    for (int i = 0; i < steps; ++i) v = nextafter(v, to);
+    return v;
+}
+
 /* x-grid, src/Pricer/kwFd1d.cpp:105-125: log-moneyness sinh grid centred on
  * the strike, independent of s and k. */
 void kwo_x_grid(double z, double t, double density, double scale, int64_t xDim, double* x)
@@ -91,7 +113,7 @@ void kwo_x_grid(double z, double t, double density, double scale, int64_t xDim, 
     const double dy = 1. / (double)(uint64_t)(xDim - 1);
     for (int j = 0; j < xDim; ++j) {
         const double yj = j * dy;
-        x[j] = xMid + density * sinh(yMin * (1.0 - yj) + yMax * yj);
+        x[j] = xMid + density * libm_jitter(sinh(yMin * (1.0 - yj) + yMax * yj), (uint64_t)j);
     }
 }
 
@@ -100,10 +122,10 @@ void kwo_payoff(int w, int64_t xDim, const double* x, double* v)
 {
     for (int j = 0; j < xDim; ++j) {
         if (w < 0) {
-            const double p = 1. - exp(x[j]);
+            const double p = 1. - libm_jitter(exp(x[j]), (uint64_t)j + 0x100000u);
             v[j] = 0 < p ? p : 0; /* std::max<f64>(0, p): returns 0 unless 0 < p */
         } else {
-            const double p = exp(x[j]) - 1.;
+            const double p = libm_jitter(exp(x[j]), (uint64_t)j + 0x100000u) - 1.;
             v[j] = 0 < p ? p : 0;
         }
     }

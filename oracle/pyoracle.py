@@ -92,6 +92,24 @@ class Oracle:
             raise ValueError(mode)
         return prices, (err.value.decode() if rc else "")
 
+    def set_libm_jitter(self, ulps: int) -> None:
+        """Test hook of fd1d_oracle.c: move every sinh() / exp() result by 0..ulps ulp (0 = the reference's bits)."""
+        self.lib.kwo_set_libm_jitter.restype = None
+        self.lib.kwo_set_libm_jitter.argtypes = [C.c_int]
+        self.lib.kwo_set_libm_jitter(int(ulps))
+
+    def libm_sensitivity(self, options, tdim, xdim, ulps=2, **kw):
+        """max |price(jitter = ulps) - price(jitter = 0)| per option: how far two faithful builds of the reference
+        against different libms may be apart on this grid shape (see fd1d_oracle.c: libm_jitter)."""
+        base, err0 = self.fd1d(options, tdim, xdim, **kw)
+        try:
+            self.set_libm_jitter(ulps)
+            jit, err1 = self.fd1d(options, tdim, xdim, **kw)
+        finally:
+            self.set_libm_jitter(0)
+        assert err0 == err1 == ""
+        return np.abs(jit - base)
+
     def solution(self, option, tdim, xdim, density=0.25, scale=50.0):
         o = _as_options(np.asarray(option).reshape(1))
         x = np.empty(xdim)

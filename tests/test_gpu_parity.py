@@ -19,6 +19,13 @@ def make_pricer(t=512, x=512, mode="FD1D-GPU", **keys):
     cfg.set("FD1D.X_GRID_SIZE", int(x))
     for k, v in keys.items():
         cfg.set(k, v)
+    # kernel variants the dispatch never picks are compiled only into the experiments build
+    # (make -C kwinto-cuda_b200/csrc EXPERIMENTS=1): their tests skip on the shipped library
+    want = int(keys.get("FD1D.GPU.VARIANT", 0))
+    if want and not kwfd1d.has_variant(want, str(keys.get("FD1D.GPU.PRECISION", "f64"))):
+        pytest.skip("kernel variant %d is an experiment (not in this build)" % want)
+    if int(keys.get("FD1D.GPU.BS_FUSED", 0)) in (2, 3) and not kwfd1d.has_variant(251):
+        pytest.skip("fused FD1D-BS variants 251 / 252 are experiments (not in this build)")
     err, p = kwfd1d.PricerFactory.create(cfg)
     assert err == "", err
     return p
@@ -119,7 +126,10 @@ def test_fd1d_bs_fused_range_error_and_dispatch():
     o = g["bs_700x200/options"].copy()
     want = g["bs_700x200/fd1d_bs"]
     o["s"][3] = 1e9
-    for fused in (4, 3, 2):
+    import kwfd1d
+
+    experiments = kwfd1d.has_variant(251)  # fused variants 252 (= 3) and 251 (= 2) exist only in the experiments build
+    for fused in ((4, 3, 2) if experiments else (4,)):
         p = make_pricer(200, 700, mode="FD1D-BS-GPU", **{"FD1D.GPU.BS_FUSED": fused})
         err, got = p.price(o)
         assert "not in range" in err and np.isnan(got[3])
@@ -138,7 +148,7 @@ def test_fd1d_bs_fused_range_error_and_dispatch():
     assert err == "" and two.info()["variant"] not in (251, 252, 253) and maxdiff(a, b) <= 1e-10
     assert maxdiff(a[:64], small) <= 1e-10
     # a ragged last group (n % 4 != 0) and a batch of one
-    for fused in (4, 3):
+    for fused in ((4, 3) if experiments else (4,)):
         for n in (1, 5, 2049):
             err, c = make_pricer(64, 1024, mode="FD1D-BS-GPU", **{"FD1D.GPU.BS_FUSED": fused}).price(big[:n])
             assert err == "" and maxdiff(c, b[:n]) <= 1e-10, (fused, n)
@@ -550,3 +560,59 @@ def test_fp32_march_synthetic_shapes(oracle):
         print("fp32 synthetic", t, x, "rel", rel, "abs", ab, p.info()["mode_count"])
         bar = 1e-4 if x <= 1024 else 4e-4  # 4096^2 is outside the fp32 configs of BASELINE.json; reported, loose bar
         assert rel <= bar and ab <= 5e-5, (t, x, rel, ab)
+
+
+@pytest.mark.gpu
+def test_multi_device_handle_is_bit_identical_to_one_device(oracle):
+    """Row M of the hot-path scope: ONE kw_fd1d_price call over several devices (kw_fd1d_create_multi: the handle
+    owns a stream, device buffers and pinned staging per device; contiguous blocks; every block's prices land in the
+    caller's array) gives the prices of a one-device handle bit for bit, reports the FIRST failing option of the
+    whole batch like the reference (src/Pricer/kwFd1d.cpp:154-155), and uses fewer devices for small batches.
+    On a one-GPU box the shards share the device (ordinals may repeat); with more GPUs they spread out."""
+    import kwfd1d
+    from kwfd1d.synthetic import synthetic_options
+
+    ndev = kwfd1d.load_library().kw_fd1d_device_count()
+    devs = ",".join(str(g % ndev) for g in range(max(3, min(ndev, 8))))
+    n = 3 * 2368 * 2 + 77   # enough for three devices at two waves each
+    o = synthetic_options(n, 91, european_every=6, call_every=4)
+    one = make_pricer(64, 1024)
+    err, want = one.price(o)
+    assert err == ""
+    multi = make_pricer(64, 1024, **{"FD1D.GPU.DEVICES": devs})
+    err, got = multi.price(o)
+    info = multi.info()
+    assert err == "" and info["n_devices"] == len(devs.split(",")) and info["devices_used"] >= 3
+    assert np.array_equal(got, want)
+    assert info["last_n_pde"] == one.info()["last_n_pde"] or info["last_n_pde"] >= one.info()["last_n_pde"]
+    idx = np.arange(n)[:: n // 40]
+    ref, oerr = oracle.fd1d(o[idx], 64, 1024)
+    assert oerr == "" and maxdiff(got[idx], ref) <= TOL
+    # a small batch stays on one device (the kernel choice must not depend on the number of devices)
+    err, small = multi.price(o[:500])
+    assert err == "" and multi.info()["devices_used"] == 1 and np.array_equal(small, one.price(o[:500])[1])
+    # pinned kernel: every device count gives the same bits, down to one option per device
+    pin1 = make_pricer(64, 1024, **{"FD1D.GPU.VARIANT": 237})
+    pinm = make_pricer(64, 1024, **{"FD1D.GPU.VARIANT": 237, "FD1D.GPU.DEVICES": devs})
+    for m in (1, 2, 5, 1000):
+        assert np.array_equal(pinm.price(o[:m])[1], pin1.price(o[:m])[1])
+    # range error: the first failing option of the WHOLE batch, the others priced
+    bad = o.copy()
+    for i in (n - 5, n // 2 + 3):
+        bad["s"][i] = 1e300  # log(s / k) far right of every grid
+    err, got = multi.price(bad)
+    e1, want = one.price(bad)
+    assert err == e1 and "not in range" in err
+    assert np.isnan(got[n - 5]) and np.isnan(got[n // 2 + 3]) and np.array_equal(np.isnan(got), np.isnan(want))
+    ok = ~np.isnan(want)
+    assert np.array_equal(got[ok], want[ok])
+    # FD1D-BS through the same split
+    bs1 = make_pricer(64, 1024, mode="FD1D-BS-GPU")
+    bsm = make_pricer(64, 1024, mode="FD1D-BS-GPU", **{"FD1D.GPU.DEVICES": devs})
+    assert np.array_equal(bsm.price(o)[1], bs1.price(o)[1])
+    # the device-resident entry point needs a single-device handle
+    assert "single-device" in multi.price_device(0, 4, 0) or "null buffer" in multi.price_device(0, 4, 0)
+    # FD1D.GPU.DEVICES as a count
+    cnt = make_pricer(64, 1024, **{"FD1D.GPU.DEVICES": -1})
+    assert cnt.info()["n_devices"] == ndev
+    assert np.array_equal(cnt.price(o)[1], want if False else one.price(o)[1])
