@@ -255,10 +255,8 @@ struct KeyHash {
             return h;
         };
         uint64_t b[4];
-        memcpy(&b[0], &o.t, 8);
-        memcpy(&b[1], &o.r, 8);
-        memcpy(&b[2], &o.q, 8);
-        memcpy(&b[3], &o.z, 8);
+        const double f[4] = {o.t + 0.0, o.r + 0.0, o.q + 0.0, o.z + 0.0};  // -0.0 == +0.0 in KeyEq: hash them alike
+        memcpy(b, f, sizeof b);
         uint64_t h = 0x243f6a8885a308d3ull;
         for (int i = 0; i < 4; ++i) h = mix(h, b[i] * 0xff51afd7ed558ccdull);
         h = mix(h, ((uint64_t)o.e << 8) | (uint8_t)o.w);

@@ -40,13 +40,18 @@ __device__ __forceinline__ uint64_t chain_mix(uint64_t h, uint64_t v)
     return h;
 }
 
+// Bit pattern of a key field for hashing.  chain_same compares with ==, as the reference's std::tie comparison
+// does (src/Pricer/kwFd1d.cpp:33-35), and -0.0 == +0.0: both zeros must hash alike or a chain with q = -0.0 and
+// one with q = +0.0 would become two PDEs where the reference solves one.  x + 0.0 is +0.0 for either zero.
+__device__ __forceinline__ uint64_t chain_bits(double x) { return (uint64_t)__double_as_longlong(x + 0.0); }
+
 __device__ __forceinline__ uint32_t chain_hash(const kw_option& o)
 {
     uint64_t h = 0x243f6a8885a308d3ull;
-    h = chain_mix(h, (uint64_t)__double_as_longlong(o.t) * 0xff51afd7ed558ccdull);
-    h = chain_mix(h, (uint64_t)__double_as_longlong(o.r) * 0xff51afd7ed558ccdull);
-    h = chain_mix(h, (uint64_t)__double_as_longlong(o.q) * 0xff51afd7ed558ccdull);
-    h = chain_mix(h, (uint64_t)__double_as_longlong(o.z) * 0xff51afd7ed558ccdull);
+    h = chain_mix(h, chain_bits(o.t) * 0xff51afd7ed558ccdull);
+    h = chain_mix(h, chain_bits(o.r) * 0xff51afd7ed558ccdull);
+    h = chain_mix(h, chain_bits(o.q) * 0xff51afd7ed558ccdull);
+    h = chain_mix(h, chain_bits(o.z) * 0xff51afd7ed558ccdull);
     h = chain_mix(h, ((uint64_t)o.e << 8) | (uint8_t)o.w);
     return (uint32_t)(h ^ (h >> 32));
 }

@@ -45,73 +45,109 @@ inline std::string optionAsString(const Option& o)
     return os.str();
 }
 
-struct PriceStats {  // what printPricesStats computes (src/Utils/kwPortfolio.cpp:101-163)
+struct PriceStats {  // the figures of the reference's "Price Statistics" block (src/Utils/kwPortfolio.cpp:148-160)
     f64 rmse = 0, rrmse = 0, mae = 0, mre = 0;
     Option maeAsset{}, mreAsset{};
     std::uint64_t total = 0;
+};
+
+// Population spread sqrt(E[x^2] - E[x]^2) and the running maximum of a stream of deviations, with the asset
+// that produced the maximum.  (The two-sum form, not Welford's, is what reproduces the reference's printed digits.)
+class DeviationStats {
+    f64 m_sum = 0, m_sumSq = 0, m_max = 0;
+    std::uint64_t m_n = 0;
+    Option m_worst{};
+
+public:
+    void add(f64 x, const Option& asset)
+    {
+        if (x > m_max) {
+            m_max = x;
+            m_worst = asset;
+        }
+        m_sum += x;
+        m_sumSq += x * x;
+        ++m_n;
+    }
+    std::uint64_t count() const { return m_n; }
+    f64 max() const { return m_max; }
+    const Option& worst() const { return m_worst; }
+    f64 spread() const
+    {
+        const f64 mean = m_sum / m_n;
+        return std::sqrt(m_sumSq / m_n - mean * mean);
+    }
 };
 
 class Portfolio {
     std::vector<Option> m_assets;
     std::vector<f64> m_prices;
 
+    // One CSV column the loader needs: its header name, the one-letter tag of the reference's error message, and
+    // what a cell does to the row being built.  The reference ignores number-parse errors
+    // (src/Utils/kwPortfolio.cpp:64-69); so do the setters.
+    struct Row {
+        Option asset{};
+        f64 price = 0;
+    };
+    struct Column {
+        const char* name;
+        char tag;
+        void (*set)(Row&, const std::string&);
+        int index = -1;
+    };
+    static std::vector<Column> columns()
+    {
+        return {
+            {"exercise", 'e', [](Row& r, const std::string& c) { r.asset.e = c == "a" ? 1 : 0; }},
+            {"strike", 'k', [](Row& r, const std::string& c) { parseNumber(c, r.asset.k); }},
+            {"dividend_rate", 'q', [](Row& r, const std::string& c) { parseNumber(c, r.asset.q); }},
+            {"interest_rate", 'r', [](Row& r, const std::string& c) { parseNumber(c, r.asset.r); }},
+            {"spot", 's', [](Row& r, const std::string& c) { parseNumber(c, r.asset.s); }},
+            {"expiry", 't', [](Row& r, const std::string& c) { parseNumber(c, r.asset.t); }},
+            {"price", 'v', [](Row& r, const std::string& c) { parseNumber(c, r.price); }},
+            {"parity", 'w', [](Row& r, const std::string& c) { r.asset.w = c == "c" ? +1 : -1; }},
+            {"volatility", 'z', [](Row& r, const std::string& c) { parseNumber(c, r.asset.z); }},
+        };
+    }
+    static void chomp(std::string& line)
+    {
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+    }
+
+    // Portfolio::load's parser (src/Utils/kwPortfolio.cpp:19-83): header names -> column indices, then one Option
+    // and one reference price per row.  Columns may come in any order; unknown columns are skipped.
     Error parse(std::istream& src)
     {
-        int e, k, q, r, s, t, v, w, z;
-        {
-            std::string header;
-            std::getline(src, header);
-            if (!header.empty() && header.back() == '\r') header.pop_back();
-            int i = 0;
-            e = k = q = r = s = t = v = w = z = -1;
-            for (const auto& colName : splitLine(header, ',')) {
-                if (colName == "exercise")
-                    e = i;
-                else if (colName == "strike")
-                    k = i;
-                else if (colName == "dividend_rate")
-                    q = i;
-                else if (colName == "interest_rate")
-                    r = i;
-                else if (colName == "spot")
-                    s = i;
-                else if (colName == "expiry")
-                    t = i;
-                else if (colName == "price")
-                    v = i;
-                else if (colName == "parity")
-                    w = i;
-                else if (colName == "volatility")
-                    z = i;
-                ++i;
-            }
-            if (e == -1 || k == -1 || q == -1 || r == -1 || s == -1 || t == -1 || v == -1 || w == -1 || z == -1) {
-                std::stringstream error;
-                error << "Portfolio::load : Some option data is missing: e=" << e << ", k=" << k << ", q=" << q
-                      << ", r=" << r << ", s=" << s << ", t=" << t << ", v=" << v << ", w=" << w << ", z=" << z;
-                return error.str();
-            }
+        auto cols = columns();
+        std::string header;
+        std::getline(src, header);
+        chomp(header);
+        const auto names = splitLine(header, ',');
+        size_t need = 0;
+        bool missing = false;
+        for (auto& col : cols) {
+            for (size_t i = 0; i < names.size(); ++i)
+                if (names[i] == col.name) col.index = (int)i;
+            missing = missing || col.index < 0;
+            need = std::max(need, (size_t)(col.index + 1));
         }
-        const size_t need = (size_t)std::max({e, k, q, r, s, t, v, w, z}) + 1;
+        if (missing) {
+            // the reference's message lists every column tag with the index it found (-1 = absent)
+            std::stringstream error;
+            error << "Portfolio::load : Some option data is missing: ";
+            for (size_t c = 0; c < cols.size(); ++c) error << (c ? ", " : "") << cols[c].tag << "=" << cols[c].index;
+            return error.str();
+        }
         for (std::string line; std::getline(src, line);) {
-            if (!line.empty() && line.back() == '\r') line.pop_back();
+            chomp(line);
             if (line.empty()) continue;
-            auto vals = splitLine(line, ',');
-            if (vals.size() < need) return "Portfolio::load : Short row '" + line + "'";
-            Option asset{};
-            // the reference ignores parse errors (src/Utils/kwPortfolio.cpp:64-69); so do we
-            parseNumber(vals[k], asset.k);
-            parseNumber(vals[q], asset.q);
-            parseNumber(vals[r], asset.r);
-            parseNumber(vals[t], asset.t);
-            parseNumber(vals[s], asset.s);
-            parseNumber(vals[z], asset.z);
-            asset.e = vals[e] == "a" ? 1 : 0;
-            asset.w = vals[w] == "c" ? +1 : -1;
-            m_assets.push_back(asset);
-            f64 price = 0;
-            parseNumber(vals[v], price);
-            m_prices.push_back(price);
+            const auto cells = splitLine(line, ',');
+            if (cells.size() < need) return "Portfolio::load : Short row '" + line + "'";
+            Row row;
+            for (const auto& col : cols) col.set(row, cells[(size_t)col.index]);
+            m_assets.push_back(row.asset);
+            m_prices.push_back(row.price);
         }
         return "";
     }
@@ -144,37 +180,29 @@ public:
         return "";
     }
 
-    // the arithmetic of printPricesStats, src/Utils/kwPortfolio.cpp:101-146, over [first, first + count)
+    // The figures of printPricesStats (src/Utils/kwPortfolio.cpp:101-146) over the assets [first, first + count):
+    // absolute and relative deviation of `prices` from the file's reference prices, assets whose reference price is
+    // below `tolerance` left out (the reference hard-wires 0.5, :110).
     PriceStats stats(const std::vector<f64>& prices, f64 tolerance = 0.5, size_t first = 0,
                      size_t count = (size_t)-1) const
     {
-        f64 absDiffSum1 = 0, absDiffSum2 = 0, relDiffSum1 = 0, relDiffSum2 = 0;
-        PriceStats st;
         const size_t end = std::min(m_prices.size(), count == (size_t)-1 ? m_prices.size() : first + count);
+        DeviationStats absolute, relative;
         for (size_t j = first; j < end; j++) {
-            const auto& wantPrice = m_prices[j];
-            const auto gotPrice = prices[j - first];
-            if (wantPrice < tolerance) continue;
-            const double absDiff = std::abs(wantPrice - gotPrice);
-            const double relDiff = absDiff / wantPrice;
-            if (absDiff > st.mae) {
-                st.mae = absDiff;
-                st.maeAsset = m_assets[j];
-            }
-            if (relDiff > st.mre) {
-                st.mre = relDiff;
-                st.mreAsset = m_assets[j];
-            }
-            absDiffSum1 += absDiff;
-            absDiffSum2 += absDiff * absDiff;
-            relDiffSum1 += relDiff;
-            relDiffSum2 += relDiff * relDiff;
-            st.total++;
+            const f64 want = m_prices[j];
+            if (want < tolerance) continue;
+            const f64 dev = std::abs(want - prices[j - first]);
+            absolute.add(dev, m_assets[j]);
+            relative.add(dev / want, m_assets[j]);
         }
-        const auto absDiffMean = absDiffSum1 / st.total;
-        st.rmse = std::sqrt(absDiffSum2 / st.total - absDiffMean * absDiffMean);
-        const auto relDiffMean = relDiffSum1 / st.total;
-        st.rrmse = std::sqrt(relDiffSum2 / st.total - relDiffMean * relDiffMean);
+        PriceStats st;
+        st.total = absolute.count();
+        st.rmse = absolute.spread();
+        st.rrmse = relative.spread();
+        st.mae = absolute.max();
+        st.mre = relative.max();
+        st.maeAsset = absolute.worst();
+        st.mreAsset = relative.worst();
         return st;
     }
 

@@ -616,3 +616,21 @@ def test_multi_device_handle_is_bit_identical_to_one_device(oracle):
     cnt = make_pricer(64, 1024, **{"FD1D.GPU.DEVICES": -1})
     assert cnt.info()["n_devices"] == ndev
     assert np.array_equal(cnt.price(o)[1], want if False else one.price(o)[1])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("compress", [1, 2])
+def test_signed_zero_dividend_is_one_chain(compress, oracle):
+    """q = -0.0 and q = +0.0 compare equal in the reference's chain key (std::tie, src/Pricer/kwFd1d.cpp:33-35), so
+    such options share ONE PDE; the hash of the device-side (1) and host-side (2) grouping must not split them."""
+    from kwfd1d.synthetic import synthetic_options
+
+    o = synthetic_options(64, 9)
+    o["q"] = 0.0
+    o["t"], o["r"], o["z"] = 0.75, 0.04, 0.3   # one chain; strikes differ
+    o["q"][::2] = -0.0
+    p = make_pricer(128, 512, **{"FD1D.GPU.COMPRESS": compress, "FD1D.GPU.VARIANT": 101})
+    err, got = p.price(o)
+    assert err == "" and p.info()["last_n_pde"] == 1, p.info()["last_n_pde"]
+    want, oerr = oracle.fd1d(o, 128, 512)
+    assert oerr == "" and maxdiff(got, want) <= TOL

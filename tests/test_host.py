@@ -156,3 +156,20 @@ def test_stage_swizzle_is_a_conflict_free_permutation():
                 for i in range(8):
                     banks = [swz((lane * nch + c) * 8 + i) % 16 for lane in range(half, half + 16)]
                     assert max(banks.count(b) for b in banks) <= worst_allowed
+
+
+def test_gpu_pricer_header_compiles_against_the_reference_tree():
+    """inside the reference, kwFd1dGpu.h is compiled with -DKW_WITH_REFERENCE against the
+    reference's own Core/Pricer headers (kw::Pricer src/Pricer/kwPricer.h:12-22, factory shape
+    src/Pricer/kwPricerFactory.h:15-41).  Pinned here where the reference tree is mounted (this container; the GPU
+    box has no /root/reference)."""
+    ref = "/root/reference/src"
+    if not os.path.isdir(ref):
+        pytest.skip("reference tree not mounted")
+    src = ('#include "kw/kwFd1dGpu.h"\n'
+           "int main() { kw::Config c; kw::sPtr<kw::Pricer> p; auto e = kw::GpuPricerFactory::create(c, p);"
+           " std::vector<kw::Option> a; std::vector<double> v; return (int)e.size(); }\n")
+    r = subprocess.run(["g++", "-std=c++20", "-fsyntax-only", "-DKW_WITH_REFERENCE", "-I", ref,
+                        "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "kwinto-cuda_b200", "host"),
+                        "-x", "c++", "-"], input=src, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
