@@ -83,7 +83,7 @@ typedef struct kw_fd1d_config {
     int32_t bs_fused;    /* FD1D.GPU.BS_FUSED, kw_fd1d_price_bs only.  0 (default): batches of a device wave  */
                          /* or more (fp64, 512 < x <= 1024) are priced by ONE launch in which every warp     */
                          /* marches its chain as given and then the European copy, with one set-up and one   */
-                         /* tensor-memory copy of the coefficients (variant 253); other batches: two solves, */
+                         /* tensor-memory copy of the coefficients (variant 257); other batches: two solves, */
                          /* as the reference.  1: always two solves.  4: variant 253 for every batch size.   */
                          /* Measured experiments with the same prices: 3 = the two marches side  */
                          /* by side in warps w and w + 4 (variant 252), 2 = both in one warp's step (251)    */

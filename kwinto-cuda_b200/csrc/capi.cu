@@ -135,9 +135,9 @@ const RegVariant g_variants[] = {
     KW_VARIANT_IW(237, 4, 2),                  // x <= 1024: Layout W with independent warps (fd1d_iw.cuh): warp-level set-up, no CTA
                                                // barrier, PDEs handed out by an atomic counter, rotated split march (23.9 ms)
     KW_VARIANT(201, 8, 128, 3, false, false),  // x <= 1024, CTA per PDE (batches below one wave of Layout W)
-    KW_VARIANT_WIDE(331, 2, false),            // x <= 2048: Layout W over two warps per PDE
+    KW_VARIANT_WIDES(336, 2),                  // x <= 2048: Layout W over two warps per PDE, rotated split march (15.65 vs 17.7 ms)
     KW_VARIANT(301, 8, 256, 1, false, false),  // x <= 2048, CTA per PDE (small batches)
-    KW_VARIANT_WIDES(436, 4),                  // x <= 4096: Layout W over four warps per PDE, split chunk-pair phases (34.8 vs 36.0 ms)
+    KW_VARIANT_WIDES(436, 4),                  // x <= 4096: Layout W over four warps per PDE, rotated split march (31.3 vs 36.0 ms)
     KW_VARIANT(401, 8, 512, 1, true, true),    // x <= 4096, CTA per PDE (small batches)
     // fp32 march (fp64 set-up): FD1D.GPU.PRECISION = f32
     KW_VARIANT_F32(1001, 8, 32, 16),
@@ -169,7 +169,7 @@ const RegVariant g_variants[] = {
     KW_VARIANT_WRT(235, 2),  // 233 with the scan-level count as a run-time value: one march loop instead of five
     KW_VARIANT_W2(241, 2, false),  // v in tensor memory, floor from shared memory
     KW_VARIANT_W2(242, 2, true),
-    KW_VARIANT_WIDES(336, 2),                  // 331 with split chunk-pair phases (18.3 vs 17.7 ms)
+    KW_VARIANT_WIDE(331, 2, false),            // the round-1 two-warp kernel
     KW_VARIANT(302, 8, 256, 2, true, true),
     KW_VARIANT_WIDE(431, 4, false),            // the round-1 four-warp kernel
     KW_VARIANT(402, 8, 512, 1, true, false),
@@ -177,15 +177,17 @@ const RegVariant g_variants[] = {
 #endif
 };
 // fused FD1D-BS marches (one set-up and one tensor-memory copy of a~, g~, D for the solve as given and the
-// solve of the European copy).  253 / 153 (default where they apply; fd1d_warp.cuh, BS = 2): every warp marches its
-// chain as given, then the European copy.  Experiments: 252 (FD1D.GPU.BS_FUSED = 3; BS = 1): eight warps per CTA,
+// solve of the European copy).  257 (fd1d_iw.cuh, BS) / 153 (fd1d_warp.cuh, BS = 2), default where they apply: every
+// warp marches its chain as given, then the European copy.  Experiments: 252 (FD1D.GPU.BS_FUSED = 3; BS = 1): eight warps per CTA,
 // warp w marches PDE w as given while warp w + 4 marches the European copy; 251 (FD1D.GPU.BS_FUSED = 2;
 // fd1d_warp_bs.cuh): both solutions in one warp's step (instruction-cache bound, slower than two solves).
-const RegVariant g_bs2_variant = {253, KW_FD1D_F64, 8, 128, 2, false, false, fd1d_warp_kernel<4, 2, false, true, 2, true>,
-                                  WarpSmem<4>::bytes(), 256, 4};
+const RegVariant g_bs2_variant = {257, KW_FD1D_F64, 8, 128, 2, false, false, fd1d_iw_kernel<4, 2, true>,
+                                  IwSmem<4>::bytes(), 256, 4};  // 512 < x <= 1024: the independent-warp kernel, BS = true
 const RegVariant g_bs2n2_variant = {153, KW_FD1D_F64, 8, 64, 2, false, false, fd1d_warp_kernel<2, 2, false, true, 2, true>,
                                     WarpSmem<2>::bytes(), 128, 4};  // 256 < x <= 512, two chunks per lane
 #ifdef KW_EXPERIMENTS
+const RegVariant g_bs253_variant = {253, KW_FD1D_F64, 8, 128, 2, false, false, fd1d_warp_kernel<4, 2, false, true, 2, true>,
+                                    WarpSmem<4>::bytes(), 256, 4};  // round 1's fused kernel (CTA-cooperative set-up)
 const RegVariant g_bs_variant = {252, KW_FD1D_F64, 8, 256, 1, false, false, fd1d_warp_kernel<4, 1, false, true, 1, true>,
                                  WarpSmem<4, 256>::bytes(), 256, 4};
 const RegVariant g_bs1_variant = {251, KW_FD1D_F64, 8, 128, 2, false, false, fd1d_warp_bs_kernel<2>,
@@ -562,16 +564,37 @@ int compress_on_device(kw_fd1d_handle* h, Fd1dBatch& B, const kw_option* d_opts,
     return KW_FD1D_OK;
 }
 
+// a copy of the options with the exercise flag cleared (src/Pricer/kwFd1d_BlackScholes.cpp:21-28)
+__global__ void european_copy_kernel(const kw_option* in, kw_option* out, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    kw_option o = load_option(in + i);
+    o.e = 0;
+    out[i] = o;
+}
+
+// options already on the device (`d_opts_p`, copied from `assets`) -> device prices in `d_out` on the handle's
+// stream; no final sync.  `european`: host-side compression must group by the key with e = 0.
+int price_resident(kw_fd1d_handle* h, const kw_option* assets, size_t n, const kw_option* d_opts_p, double* d_out,
+                   double* d_out_eu = nullptr, bool european = false);
+
 // host assets -> device prices in `d_out` (n doubles) on the handle's stream; no final sync
 int price_to_device(kw_fd1d_handle* h, const kw_option* assets, size_t n, DevBuf<kw_option>& d_opts,
                     double* d_out, double* d_out_eu = nullptr)
 {
     KW_CUDA(h, d_opts.reserve(n));
-    KW_CUDA(h, h->d_status.reserve(16));
     KW_CUDA(h, cudaMemcpyAsync(d_opts.p, assets, n * sizeof(kw_option), cudaMemcpyHostToDevice, h->stream));
+    return price_resident(h, assets, n, d_opts.p, d_out, d_out_eu);
+}
+
+int price_resident(kw_fd1d_handle* h, const kw_option* assets, size_t n, const kw_option* d_opts_p, double* d_out,
+                   double* d_out_eu, bool european)
+{
+    KW_CUDA(h, h->d_status.reserve(16));
     Fd1dBatch B;
     memset(&B, 0, sizeof B);
-    B.opts = d_opts.p;
+    B.opts = d_opts_p;
     B.prices = d_out;
     B.prices_eu = d_out_eu;  // non-null: the fused FD1D-BS march (both solutions of every chain)
     B.status = h->d_status.p;
@@ -582,11 +605,16 @@ int price_to_device(kw_fd1d_handle* h, const kw_option* assets, size_t n, DevBuf
     B.max_mode = h->cfg.exact == 0 ? 4 : (h->cfg.exact == 1 ? 1 : 0);
     h->dev_compressed = false;
     if (h->cfg.compress == 1 && h->layout == KW_FD1D_LAYOUT_REG) {
-        if (int rc = compress_on_device(h, B, d_opts.p, n, h->stream)) return rc;
+        if (int rc = compress_on_device(h, B, d_opts_p, n, h->stream)) return rc;
     } else if (h->cfg.compress) {
         size_t m;
         uint32_t *rep, *start, *csr;
-        if (int rc = compress(h, assets, n, m, rep, start, csr)) return rc;
+        std::vector<kw_option> euro;
+        if (european) {  // host-side grouping (FD1D.GPU.COMPRESS = 2 / the SoA layout) of the European copies
+            euro.assign(assets, assets + n);
+            for (auto& o : euro) o.e = 0;
+        }
+        if (int rc = compress(h, european ? euro.data() : assets, n, m, rep, start, csr)) return rc;
         if (m < n) {
             KW_CUDA(h, h->d_rep.reserve(m));
             KW_CUDA(h, h->d_start.reserve(m + 1));
@@ -962,16 +990,17 @@ int kw_fd1d_price_bs(kw_fd1d_handle* h, const kw_option* assets, size_t n, doubl
         }
         return rc;
     }
-    // 2. FD on European copies (:21-28)
-    std::vector<kw_option> euro(assets, assets + n);
-    for (auto& o : euro) o.e = 0;
-    if (int rc = price_to_device(h, euro.data(), n, h->d_opts2, h->d_prices2.p)) return rc;
+    // 2. FD on European copies (:21-28): the copy is made on the device from the options already there
+    KW_CUDA(h, h->d_opts2.reserve(n));
+    european_copy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_opts.p, h->d_opts2.p, n);
+    h->launches += 1;
+    if (int rc = price_resident(h, assets, n, h->d_opts2.p, h->d_prices2.p, nullptr, /*european=*/true)) return rc;
     // 3. + (BS - FD_euro) (:30-40)
     bs_combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_opts2.p, n, h->d_prices.p, h->d_prices2.p);
     h->launches += 1;
     KW_CUDA(h, cudaGetLastError());
     KW_CUDA(h, cudaMemcpyAsync(prices, h->d_prices.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    return check_status(h, h->stream, euro.data());
+    return check_status(h, h->stream, assets);
 }
 
 int kw_fd1d_price_device(kw_fd1d_handle* h, const kw_option* d_assets, size_t n, double* d_prices, void* stream)
@@ -1244,7 +1273,7 @@ int kw_fd1d_has_variant(int32_t id, int32_t precision)
         if (g_variants[i].id == id && g_variants[i].prec == precision) return 1;
     if (precision == KW_FD1D_F64 && (id == g_bs2_variant.id || id == g_bs2n2_variant.id)) return 1;
 #ifdef KW_EXPERIMENTS
-    if (precision == KW_FD1D_F64 && (id == g_bs_variant.id || id == g_bs1_variant.id)) return 1;
+    if (precision == KW_FD1D_F64 && (id == g_bs_variant.id || id == g_bs1_variant.id || id == g_bs253_variant.id)) return 1;
 #endif
     return 0;
 }

@@ -36,7 +36,13 @@ struct IwSmem {
     static constexpr size_t bytes() { return sizeof(double) * (size_t)(4 * (N + SCR)); }
 };
 
-template <int NCH, int MINB>
+// BS: the fused march of the control-variate pricer "FD1D-BS" (Fd1d_BlackScholes_Pricer::price, reference
+// src/Pricer/kwFd1d_BlackScholes.cpp:15-43: the solve as given plus the solve of a European copy of every chain).
+// Both solves share the grid and the hoisted LU, so ONE set-up and ONE tensor-memory copy of a~, g~, D serve both:
+// the warp marches its chain as given, prices into B.prices, re-creates the payoff and marches the European copy
+// (no floor loads, compares or selects) into B.prices_eu.  A chain given as European is marched once and priced into
+// both arrays.  capi.cu adds the closed form (bs_combine_kernel).
+template <int NCH, int MINB, bool BS = false>
 __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
 {
     static_assert(NCH == 4 || NCH == 2, "4 chunks per lane (512 < x <= 1024) or 2 (256 < x <= 512)");
@@ -299,6 +305,11 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
         // inside the march loop (6 DMUL + the lane predicate per step) to save two registers
 #pragma unroll
         for (int d = 0; d < 5; ++d) asm volatile("" : "+d"(AfL[d]), "+d"(GbL[d]));
+        auto kA = [&](int c) { return Ac[c]; };
+        auto kG = [&](int c) { return Gc[c]; };
+        auto kR = [&](int c) { return R0c[c]; };
+        auto kAf = [&](int d) { return AfL[d]; };
+        auto kGb = [&](int d) { return GbL[d]; };
         // ================= how many levels carry anything (DESIGN.md "Truncation") =======================
         int levels = 0;
         {
@@ -316,8 +327,9 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
         }
 
         // ================= time march: fd1d_warp_kernel's SPLIT chunk-pair form ==========================
-        auto march = [&](auto lev_c) {
+        auto march = [&](auto lev_c, auto euro_c) {
             constexpr int LEV = decltype(lev_c)::value;
+            constexpr bool EURO = decltype(euro_c)::value;  // European copy: no floor, no compare
             double e[NCH], f[NCH];
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
@@ -340,35 +352,35 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
             auto scan = [&]() {
                 double S = e[0];
 #pragma unroll
-                for (int c = 1; c < NCH; ++c) S = fma(Ac[c], S, e[c]);
+                for (int c = 1; c < NCH; ++c) S = fma(kA(c), S, e[c]);
 #pragma unroll
                 for (int d = 0; d < LEV; ++d) {
                     const double o = __shfl_up_sync(FULL, S, 1 << d);
-                    S = fma(AfL[d], o, S);
+                    S = fma(kAf(d), o, S);
                 }
                 {
                     const double o = __shfl_up_sync(FULL, S, 1);
                     Yin[0] = lane ? o : 0.;
                 }
 #pragma unroll
-                for (int c = 1; c < NCH; ++c) Yin[c] = fma(Ac[c - 1], Yin[c - 1], e[c - 1]);
+                for (int c = 1; c < NCH; ++c) Yin[c] = fma(kA(c - 1), Yin[c - 1], e[c - 1]);
                 // backward: chunk-start values with the true forward carry, scan, chunk-exit values
 #pragma unroll
-                for (int c = 0; c < NCH; ++c) f[c] = fma(R0c[c], Yin[c], f[c]);
+                for (int c = 0; c < NCH; ++c) f[c] = fma(kR(c), Yin[c], f[c]);
                 double T = f[NCH - 1];
 #pragma unroll
-                for (int c = NCH - 2; c >= 0; --c) T = fma(Gc[c], T, f[c]);
+                for (int c = NCH - 2; c >= 0; --c) T = fma(kG(c), T, f[c]);
 #pragma unroll
                 for (int d = 0; d < LEV; ++d) {
                     const double o = __shfl_down_sync(FULL, T, 1 << d);
-                    T = fma(GbL[d], o, T);
+                    T = fma(kGb(d), o, T);
                 }
                 {
                     const double o = __shfl_down_sync(FULL, T, 1);
                     Uin[NCH - 1] = lane < 31 ? o : 0.;
                 }
 #pragma unroll
-                for (int c = NCH - 2; c >= 0; --c) Uin[c] = fma(Gc[c + 1], Uin[c + 1], f[c + 1]);
+                for (int c = NCH - 2; c >= 0; --c) Uin[c] = fma(kG(c + 1), Uin[c + 1], f[c + 1]);
             };
             // ---- true forward sweeps of the chunk pair (cA, cA + 1) from Yin
             auto fwd_pair = [&](int cA, double (&yA)[8], double (&yB)[8]) {
@@ -393,10 +405,15 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
                 tmem::ld8(tbase + T_G + 16 * cB, gB);
                 tmem::ld8(tbase + T_D + 16 * cA, dA);
                 tmem::ld8(tbase + T_D + 16 * cB, dB);
-                tmem::ld8(tbase + T_P + 16 * cA, pA);
-                tmem::ld8(tbase + T_P + 16 * cB, pB);
-                tmem::hot_wait(gA, gB, dA);
-                tmem::hot_wait(dB, pA, pB);
+                if constexpr (!EURO) {
+                    tmem::ld8(tbase + T_P + 16 * cA, pA);
+                    tmem::ld8(tbase + T_P + 16 * cB, pB);
+                    tmem::hot_wait(gA, gB, dA);
+                    tmem::hot_wait(dB, pA, pB);
+                } else {
+                    tmem::hot_wait(gA, gB);
+                    tmem::hot_wait(dA, dB);
+                }
                 double uA = Uin[cA], uB = Uin[cB];
 #pragma unroll
                 for (int i = 7; i >= 0; --i) {
@@ -404,8 +421,13 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
                     uB = fma(gB[i], uB, yB[i]);
                     const double rA = fma(dA[i], uA, -vr[8 * cA + i]);
                     const double rB = fma(dB[i], uB, -vr[8 * cB + i]);
-                    vr[8 * cA + i] = max_like_std(rA, pA[i]);
-                    vr[8 * cB + i] = max_like_std(rB, pB[i]);
+                    if constexpr (EURO) {
+                        vr[8 * cA + i] = rA;
+                        vr[8 * cB + i] = rB;
+                    } else {
+                        vr[8 * cA + i] = max_like_std(rA, pA[i]);
+                        vr[8 * cB + i] = max_like_std(rB, pB[i]);
+                    }
                 }
                 double aA[8], aB[8];
                 tmem::ld8(tbase2 + T_A + 16 * cA, aA);
@@ -454,29 +476,56 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
             }
             tmem::wait_ld();  // nothing in flight when the arrays are rewritten
         };
-        switch (levels) {
-            case 1: march(std::integral_constant<int, 1>{}); break;
-            case 2: march(std::integral_constant<int, 2>{}); break;
-            case 3: march(std::integral_constant<int, 3>{}); break;
-            case 4: march(std::integral_constant<int, 4>{}); break;
-            default: march(std::integral_constant<int, 5>{}); break;
-        }
+        auto march_levels = [&](auto euro_c) {
+            switch (levels) {
+                case 1: march(std::integral_constant<int, 1>{}, euro_c); break;
+                case 2: march(std::integral_constant<int, 2>{}, euro_c); break;
+                case 3: march(std::integral_constant<int, 3>{}, euro_c); break;
+                case 4: march(std::integral_constant<int, 4>{}, euro_c); break;
+                default: march(std::integral_constant<int, 5>{}, euro_c); break;
+            }
+        };
+        // ================= epilogue: interpolate every option of this chain ===============================
+        auto emit = [&](double* out) {
+#pragma unroll
+            for (int i = 0; i < NODES; ++i) vfin[lane * NODES + i] = vr[i];
+            __syncwarp();
+            Fd1dBatch Bo = B;
+            Bo.prices = out;
+            uint32_t q0, q1;
+            chain_range(B, my_pde, q0, q1);
+            for (uint32_t q = q0 + lane; q < q1; q += 32) {
+                const uint32_t oi = B.csr_opt ? __ldg(B.csr_opt + q) : q;
+                price_option(Bo, oi, [&](int j) { return x_node(sc, B.density, j); }, [&](int j) { return vfin[j]; });
+            }
+            __syncwarp();  // vfin is rewritten by the next emit
+        };
+        march_levels(std::false_type{});
         if (lane == 0) {
             // histogram buckets shared with Layout B: 0 = exact requested, 1 = all 5 levels, 2/3/4 = 4/3/2, 5 = 1 level
             const int bucket = B.max_mode == 0 ? 0 : (levels == 5 ? 1 : 6 - levels);
             atomicAdd(&B.status[2 + bucket], 1u);
         }
-        // ================= epilogue: interpolate every option of this chain ===============================
+        emit(B.prices);
+        if constexpr (BS) {
+            if (sc.american) {
+                // the European copy: payoff again (src/Pricer/kwFd1d.cpp:127-139, as in the set-up), same LU (still in
+                // tensor memory), no projection
+#pragma unroll 1
+                for (int c = 0; c < NCH; ++c) {
 #pragma unroll
-        for (int i = 0; i < NODES; ++i) vfin[lane * NODES + i] = vr[i];
-        __syncwarp();
-        {
-            uint32_t q0, q1;
-            chain_range(B, my_pde, q0, q1);
-            for (uint32_t q = q0 + lane; q < q1; q += 32) {
-                const uint32_t oi = B.csr_opt ? __ldg(B.csr_opt + q) : q;
-                price_option(B, oi, [&](int j) { return x_node(sc, B.density, j); }, [&](int j) { return vfin[j]; });
+                    for (int i = 0; i < 8; ++i) {
+                        const int j = lane * NODES + 8 * c + i;
+                        vfin[(8 * c + i) * 32 + lane] = j < xDim ? payoff_node_ni(sc.put, x_node_ni(sc, B.density, j)) : 0.;
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < NODES; ++i) vr[i] = vfin[i * 32 + lane];
+                __syncwarp();
+                march_levels(std::true_type{});
             }
+            emit(B.prices_eu);  // a chain given as European: one march, both arrays
         }
         __syncwarp();  // vfin is rewritten by the next PDE
     }

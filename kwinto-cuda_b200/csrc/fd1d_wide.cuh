@@ -425,8 +425,185 @@ __global__ void __launch_bounds__(128, MINB) fd1d_wide_kernel(const Fd1dBatch B,
                     }
                 }
             };
+            // SPLIT: the rotated form of fd1d_iw.cuh -- scan constants in registers, every chunk-pair phase a basic
+            // block, a~ / g~ loaded twice, and the NEXT step's scans (with their two named barriers) issued behind the
+            // last pair's local sweeps with pair 0's forward sweeps behind them, so that shuffle, shared-memory and
+            // barrier latency hides behind sweeps of the same basic block.
+            auto march_rot = [&](auto lev_c) {
+                constexpr int LEV = decltype(lev_c)::value;
+                double kA[NCH], kG[NCH], kR[NCH], kAf[LEV], kGb[LEV];
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    kA[c] = K(c);
+                    kG[c] = K(4 + c);
+                    kR[c] = K(8 + c);
+                }
+#pragma unroll
+                for (int d = 0; d < LEV; ++d) {
+                    kAf[d] = K(12 + d);
+                    kGb[d] = K(17 + d);
+                }
+                const double kPf = K(22), kPb = K(23);
+                double e[NCH], f[NCH], Yin[NCH], Uin[NCH];
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    double a8[8], g8[8];
+                    tmem::ld8(tbase + T_A + 16 * c, a8);
+                    tmem::ld8(tbase + T_G + 16 * c, g8);
+                    tmem::wait_ld_dep(a8, g8);
+                    double y[8];
+                    y[0] = vr[8 * c];
+#pragma unroll
+                    for (int i = 1; i < 8; ++i) y[i] = fma(a8[i], y[i - 1], vr[8 * c + i]);
+                    e[c] = y[7];
+                    double u = y[7];
+#pragma unroll
+                    for (int i = 6; i >= 0; --i) u = fma(g8[i], u, y[i]);
+                    f[c] = u;
+                }
+                uint32_t par = 0;  // bytes: 4 doubles per parity, flipped by every scan
+                auto scan_fwd = [&]() {
+                    double S = e[0];
+#pragma unroll
+                    for (int c = 1; c < NCH; ++c) S = fma(kA[c], S, e[c]);
+#pragma unroll
+                    for (int d = 0; d < LEV; ++d) {
+                        const double o = __shfl_up_sync(FULL, S, 1 << d);
+                        S = fma(kAf[d], o, S);
+                    }
+                    if (last_lane) sts_f64(a_myzf + par, S);
+                    double Sm1 = __shfl_up_sync(FULL, S, 1);
+                    if (first_lane) Sm1 = 0.;
+                    group_barrier<32 * NWP>(grp);
+                    double X = 0.;
+#pragma unroll
+                    for (int w = 0; w < NWP; ++w)  // the PDE's own slots only: another PDE's value times 0 may be NaN
+                        X = fma(lds_f64(a_cf + (w0 + w) * 8), lds_f64(a_zf + par + (w0 + w) * 8), X);
+                    Yin[0] = fma(kPf, X, Sm1);
+#pragma unroll
+                    for (int c = 1; c < NCH; ++c) Yin[c] = fma(kA[c - 1], Yin[c - 1], e[c - 1]);
+                };
+                auto scan_bwd = [&]() {
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) f[c] = fma(kR[c], Yin[c], f[c]);
+                    double T = f[NCH - 1];
+#pragma unroll
+                    for (int c = NCH - 2; c >= 0; --c) T = fma(kG[c], T, f[c]);
+#pragma unroll
+                    for (int d = 0; d < LEV; ++d) {
+                        const double o = __shfl_down_sync(FULL, T, 1 << d);
+                        T = fma(kGb[d], o, T);
+                    }
+                    if (first_lane) sts_f64(a_myzb + par, T);
+                    double Tp1 = __shfl_down_sync(FULL, T, 1);
+                    if (last_lane) Tp1 = 0.;
+                    group_barrier<32 * NWP>(grp);
+                    double Xb = 0.;
+#pragma unroll
+                    for (int w = 0; w < NWP; ++w)
+                        Xb = fma(lds_f64(a_cb + (w0 + w) * 8), lds_f64(a_zb + par + (w0 + w) * 8), Xb);
+                    Uin[NCH - 1] = fma(kPb, Xb, Tp1);
+#pragma unroll
+                    for (int c = NCH - 2; c >= 0; --c) Uin[c] = fma(kG[c + 1], Uin[c + 1], f[c + 1]);
+                    par ^= 32u;
+                };
+                auto fwd_load = [&](int cA, double (&aA)[8], double (&aB)[8]) {
+                    tmem::ld8(tbase + T_A + 16 * cA, aA);
+                    tmem::ld8(tbase + T_A + 16 * (cA + 1), aB);
+                    tmem::hot_wait(aA, aB);
+                };
+                auto fwd_sweep = [&](int cA, const double (&aA)[8], const double (&aB)[8], double (&yA)[8], double (&yB)[8]) {
+                    const int cB = cA + 1;
+                    yA[0] = fma(aA[0], Yin[cA], vr[8 * cA]);
+                    yB[0] = fma(aB[0], Yin[cB], vr[8 * cB]);
+#pragma unroll
+                    for (int i = 1; i < 8; ++i) {
+                        yA[i] = fma(aA[i], yA[i - 1], vr[8 * cA + i]);
+                        yB[i] = fma(aB[i], yB[i - 1], vr[8 * cB + i]);
+                    }
+                };
+                auto back_pair = [&](int cA, double (&yA)[8], double (&yB)[8]) {
+                    const int cB = cA + 1;
+                    double gA[8], gB[8], dA[8], dB[8], pA[8], pB[8];
+                    tmem::ld8(tbase + T_G + 16 * cA, gA);
+                    tmem::ld8(tbase + T_G + 16 * cB, gB);
+                    tmem::ld8(tbase + T_D + 16 * cA, dA);
+                    tmem::ld8(tbase + T_D + 16 * cB, dB);
+                    tmem::ld8(tbase + T_P + 16 * cA, pA);
+                    tmem::ld8(tbase + T_P + 16 * cB, pB);
+                    tmem::hot_wait(gA, gB, dA);
+                    tmem::hot_wait(dB, pA, pB);
+                    double uA = Uin[cA], uB = Uin[cB];
+#pragma unroll
+                    for (int i = 7; i >= 0; --i) {
+                        uA = fma(gA[i], uA, yA[i]);
+                        uB = fma(gB[i], uB, yB[i]);
+                        const double rA = fma(dA[i], uA, -vr[8 * cA + i]);
+                        const double rB = fma(dB[i], uB, -vr[8 * cB + i]);
+                        vr[8 * cA + i] = ICMP ? max_like_icmp(rA, pA[i]) : max_like_std(rA, pA[i]);
+                        vr[8 * cB + i] = ICMP ? max_like_icmp(rB, pB[i]) : max_like_std(rB, pB[i]);
+                    }
+                    double aA[8], aB[8];
+                    tmem::ld8(tbase2 + T_A + 16 * cA, aA);
+                    tmem::ld8(tbase2 + T_A + 16 * cB, aB);
+                    tmem::ld8(tbase2 + T_G + 16 * cA, gA);
+                    tmem::ld8(tbase2 + T_G + 16 * cB, gB);
+                    tmem::hot_wait(aA, aB);
+                    tmem::hot_wait(gA, gB);
+                    yA[0] = vr[8 * cA];
+                    yB[0] = vr[8 * cB];
+#pragma unroll
+                    for (int i = 1; i < 8; ++i) {
+                        yA[i] = fma(aA[i], yA[i - 1], vr[8 * cA + i]);
+                        yB[i] = fma(aB[i], yB[i - 1], vr[8 * cB + i]);
+                    }
+                    e[cA] = yA[7];
+                    e[cB] = yB[7];
+                    uA = yA[7];
+                    uB = yB[7];
+#pragma unroll
+                    for (int i = 6; i >= 0; --i) {
+                        uA = fma(gA[i], uA, yA[i]);
+                        uB = fma(gB[i], uB, yB[i]);
+                    }
+                    f[cA] = uA;
+                    f[cB] = uB;
+                };
+                // pair 0's a~ is loaded between the two halves of the scan: its forward sweeps need only Yin, so they
+                // fill the wait at the second named barrier
+                double y0A[8], y0B[8];
+                {
+                    double aA[8], aB[8];
+                    scan_fwd();
+                    fwd_load(0, aA, aB);
+                    scan_bwd();
+                    fwd_sweep(0, aA, aB, y0A, y0B);
+                }
+                for (int step = 0; step < nsteps; ++step) {
+                    if (step < B.opq_lim[0]) back_pair(0, y0A, y0B);  // always true: basic-block boundary
+                    if (step < B.opq_lim[1]) {
+                        double yA[8], yB[8], aA[8], aB[8];
+                        fwd_load(2, aA, aB);
+                        fwd_sweep(2, aA, aB, yA, yB);
+                        back_pair(2, yA, yB);
+                        scan_fwd();
+                        fwd_load(0, aA, aB);
+                        scan_bwd();
+                        fwd_sweep(0, aA, aB, y0A, y0B);  // after the last step: computed and dropped
+                    }
+                }
+            };
             // the PDE's warps share barriers, so they must agree on nothing but the step count; each picks
             // its own number of in-warp levels
+            if constexpr (SPLIT) {
+                switch (levels) {
+                    case 1: march_rot(std::integral_constant<int, 1>{}); break;
+                    case 2: march_rot(std::integral_constant<int, 2>{}); break;
+                    case 3: march_rot(std::integral_constant<int, 3>{}); break;
+                    case 4: march_rot(std::integral_constant<int, 4>{}); break;
+                    default: march_rot(std::integral_constant<int, 5>{}); break;
+                }
+            } else
             switch (levels) {
                 case 1: march(std::integral_constant<int, 1>{}); break;
                 case 2: march(std::integral_constant<int, 2>{}); break;

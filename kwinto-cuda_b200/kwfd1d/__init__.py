@@ -156,8 +156,8 @@ class Fd1dGpu_Pricer(Pricer):
     ("auto"|"reg"|"soa"), FD1D.GPU.PRECISION ("f64"), FD1D.GPU.COMPRESS (int 0/1),
     FD1D.GPU.DEVICES (int N or "0,1,..": one price() call over several GPUs), FD1D.GPU.VARIANT (int), FD1D.GPU.EXACT (int 0/1/2: 0 lets provably negligible carry terms be
     dropped, 2 keeps every term), FD1D.GPU.BS_FUSED (int, "FD1D-BS-GPU" only: 0 = fused
-    American + European march (variant 253) for batches of a device wave or more, 1 = always two solves as
-    the reference does, 4 = variant 253 for every batch size, 3 / 2 = the measured experiments 252 / 251)."""
+    American + European march (variant 257) for batches of a device wave or more, 1 = always two solves as
+    the reference does, 4 = variant 257 for every batch size, 3 / 2 = the measured experiments 252 / 251)."""
 
     _mode_bs = False
 

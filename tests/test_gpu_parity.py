@@ -87,7 +87,7 @@ def test_synthetic_golden_all_shapes():
 
 
 @pytest.mark.parametrize("key,fused,variant", [(k, f, v) for k in ("bs_1024", "bs_700x200", "bs_513x64")
-                                               for f, v in ((4, 253), (3, 252), (2, 251))] +
+                                               for f, v in ((4, 257), (3, 252), (2, 251))] +
                          [(k, 4, 153) for k in ("bs_512", "bs_300x100")])
 def test_fd1d_bs_fused_march(key, fused, variant):
     # src/Pricer/kwFd1d_BlackScholes.cpp:15-43 with both solves of a chain marched by one launch --
@@ -109,7 +109,7 @@ def test_fd1d_bs_fused_march(key, fused, variant):
     assert maxdiff(got, g[key + "/fd1d_bs"]) <= TOL, maxdiff(got, g[key + "/fd1d_bs"])
     two = make_pricer(t, x, mode="FD1D-BS-GPU", **{"FD1D.GPU.BS_FUSED": 1})
     err, got2 = two.price(o)
-    assert err == "" and two.info()["variant"] not in (153, 251, 252, 253)
+    assert err == "" and two.info()["variant"] not in (153, 251, 252, 253, 257)
     assert maxdiff(got2, g[key + "/fd1d_bs"]) <= TOL
     assert maxdiff(got, got2) <= 1e-10
     # a plain FD1D pricer of the same configuration is unaffected
@@ -139,13 +139,13 @@ def test_fd1d_bs_fused_range_error_and_dispatch():
     auto = make_pricer(64, 1024, mode="FD1D-BS-GPU")
     small_o = synthetic_options(64, 5, european_every=7)
     err, small = auto.price(small_o)
-    assert err == "" and auto.info()["variant"] not in (251, 252, 253)
+    assert err == "" and auto.info()["variant"] not in (251, 252, 253, 257)
     big = synthetic_options(2048, 5, european_every=7)
     err, a = auto.price(big)
-    assert err == "" and auto.info()["variant"] == 253
+    assert err == "" and auto.info()["variant"] == 257
     two = make_pricer(64, 1024, mode="FD1D-BS-GPU", **{"FD1D.GPU.BS_FUSED": 1})
     err, b = two.price(big)
-    assert err == "" and two.info()["variant"] not in (251, 252, 253) and maxdiff(a, b) <= 1e-10
+    assert err == "" and two.info()["variant"] not in (251, 252, 253, 257) and maxdiff(a, b) <= 1e-10
     assert maxdiff(a[:64], small) <= 1e-10
     # a ragged last group (n % 4 != 0) and a batch of one
     for fused in ((4, 3) if experiments else (4,)):
@@ -262,7 +262,7 @@ def test_wide_layout_w(x, t, n, oracle):
         p = make_pricer(t, x, **{"FD1D.GPU.EXACT": exact})
         err, got = p.price(o)
         assert err == ""
-        assert p.info()["variant"] in (331, 431), p.info()["variant"]
+        assert p.info()["variant"] in (331, 336, 431, 436), p.info()["variant"]
         assert p.info()["last_n_pde"] == n
         res[exact] = got
         bar = TOL if t * 8 >= x else 5e-9
