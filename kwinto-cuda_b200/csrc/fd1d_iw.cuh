@@ -89,7 +89,6 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
         {
             const int j0 = lane * NODES;
             double* s_v = vfin;            // [NODES][32] payoff, until the registers take it
-            double* s_m = scr;             // [4 * NCH][32] chunk maps
             double* s_k = scr + 16 * 32;   // [3 * NCH][32] chunk scalars
             // ---- grid, payoff, projection floor, rows of B (parked in tensor memory)
             double bu_carry = 0.;
@@ -153,10 +152,6 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
                         if ((i & 3) == 3) mat_normalise(m);
                     }
                     bu_carry = bu[7];
-                    s_m[(4 * c + 0) * 32 + lane] = m.m00;
-                    s_m[(4 * c + 1) * 32 + lane] = m.m01;
-                    s_m[(4 * c + 2) * 32 + lane] = m.m10;
-                    s_m[(4 * c + 3) * 32 + lane] = m.m11;
                     Lm = mat_mul(m, Lm);
                     mat_normalise(Lm);
                 }
@@ -171,21 +166,45 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
                 const Mat2 E = mat_shfl_up(Lm, 1);
                 double num = lane ? E.m00 : 1.;
                 double den = lane ? E.m10 : 0.;
+                // ---- The scan's pivots are a first guess only.  The recurrence beta_j = b_j - c_j / beta_{j-1} contracts
+                //      (d beta_j / d beta_{j-1} = c_j / beta_{j-1}^2 < 1), so run serially it forgets its rounding errors,
+                //      while the composed maps accumulate theirs over the whole grid (1e-13 relative at 4096 nodes: on stiff
+                //      grids -- few time steps, dt/dx^2 in the thousands -- that alone moved prices by 3e-9 against the
+                //      reference).  Polish: every lane re-runs the reference's recurrence over its own nodes from its
+                //      incoming pivot and hands the result to the next lane, until no incoming pivot changes any more.  Lane l
+                //      is exact after l sweeps at the latest; with the contraction, two or three sweeps do (stiff: up to ~10).
+                //      The fixed point IS the serial recurrence of src/Math/kwMath.cpp:30-38, bit for bit.
+                double pin = den == 0. ? CUDART_INF : num / den;  // pivot just before the lane's first node
+#pragma unroll 1
+                for (int sweep = 0; sweep < 34; ++sweep) {
+                    double prev = pin;
+                    bu_carry = bu_prev_lane;
+#pragma unroll 1
+                    for (int c = 0; c < NCH; ++c) {
+                        double bl[8], bb[8], bu[8];
+                        tmem::ld8(tbase + T_A + 16 * c, bl);
+                        tmem::ld8(tbase + T_G + 16 * c, bb);
+                        tmem::ld8(tbase + T_D + 16 * c, bu);
+                        tmem::wait_ld_dep(bl, bb, bu);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const double gam = (i ? bu[i > 0 ? i - 1 : 0] : bu_carry) / prev;
+                            prev = __dsub_rn(bb[i], __dmul_rn(bl[i], gam));
+                        }
+                        bu_carry = bu[7];
+                    }
+                    double pnew = __shfl_up_sync(FULL, prev, 1);
+                    if (lane == 0) pnew = CUDART_INF;
+                    const bool changed = __double_as_longlong(pnew) != __double_as_longlong(pin);
+                    pin = pnew;
+                    if (!__any_sync(FULL, changed)) break;
+                }
                 // ---- pivots inside every chunk, in the reference's order (src/Math/kwMath.cpp:32-33):
                 //      gam = au[j-1] / bet;  bet = a[j] - al[j] * gam;  1/beta replaces the diagonal in tensor memory
                 bu_carry = bu_prev_lane;
+                double prev = pin;
 #pragma unroll 1
                 for (int c = 0; c < NCH; ++c) {
-                    double prev = den == 0. ? CUDART_INF : num / den;  // the pivot just before the chunk
-                    {
-                        const double m00 = s_m[(4 * c + 0) * 32 + lane], m01 = s_m[(4 * c + 1) * 32 + lane];
-                        const double m10 = s_m[(4 * c + 2) * 32 + lane], m11 = s_m[(4 * c + 3) * 32 + lane];
-                        const double nn = fma(m00, num, m01 * den);
-                        const double dd = fma(m10, num, m11 * den);
-                        const double sn = 1. / fmax(fabs(nn), fabs(dd));
-                        num = nn * sn;
-                        den = dd * sn;
-                    }
                     double bl[8], bb[8], bu[8];
                     tmem::ld8(tbase + T_A + 16 * c, bl);
                     tmem::ld8(tbase + T_G + 16 * c, bb);

@@ -249,8 +249,9 @@ def test_tmem_variants_all_modes_and_reuse(variant, oracle):
 def test_wide_layout_w(x, t, n, oracle):
     """Grids wider than one warp can hold (fd1d_wide.cuh): the auto dispatch takes the multi-warp Layout W
     for batches that fill the device; every cross-warp carry term is kept, so all EXACT settings must
-    agree with each other and with the oracle (on these few-step fine grids the libm-driven bar is 5e-9,
-    DESIGN.md "Parity budget"), with duplicates in the batch (device-side compression) and calls/Europeans."""
+    agree with each other and with the oracle -- at the 1e-9 bar also on these stiff grids (few time steps on a fine
+    grid), since the set-up polishes the scanned pivots into the reference's serial recurrence (DESIGN.md "Parity
+    budget") -- with duplicates in the batch (device-side compression) and calls/Europeans."""
     from kwfd1d.synthetic import synthetic_options
 
     o = synthetic_options(n, 900 + x, european_every=4, call_every=3)
@@ -265,8 +266,7 @@ def test_wide_layout_w(x, t, n, oracle):
         assert p.info()["variant"] in (331, 336, 431, 436), p.info()["variant"]
         assert p.info()["last_n_pde"] == n
         res[exact] = got
-        bar = TOL if t * 8 >= x else 5e-9
-        assert maxdiff(got, want) <= bar, (x, t, exact, maxdiff(got, want))
+        assert maxdiff(got, want) <= TOL, (x, t, exact, maxdiff(got, want))
     print("wide", x, t, "exact-vs-auto", maxdiff(res[0], res[2]), "vs oracle", maxdiff(res[0], want))
     assert maxdiff(res[0], res[2]) <= 1e-11
 
@@ -351,8 +351,7 @@ def test_range_error_in_warp_layouts(x, t, n, variants, oracle):
     assert np.isnan(got[n // 2]) and np.isfinite(np.delete(got, n // 2)).all()
     good = np.delete(np.arange(n), n // 2)[:: max(1, n // 64)]
     want, oerr = oracle.fd1d(o[good], t, x)
-    bar = TOL if t * 8 >= x else 5e-9
-    assert oerr == "" and maxdiff(got[good], want) <= bar
+    assert oerr == "" and maxdiff(got[good], want) <= TOL
     # the handle recovers
     o["k"][n // 2] = 100.
     err, got = p.price(o)
@@ -461,8 +460,8 @@ def test_cpp_pricer_interface():
 def test_carry_truncation_modes(x, t, oracle):
     """FD1D.GPU.EXACT: 0 lets the kernel drop carry terms it proves < 2^-56 (modes 1..4); 2 keeps every
     term (mode 0).  The modes must agree with each other far below the parity bar, and all must meet
-    the bar.  On the (4096, 64) shape dt/dx^2 is ~2000, which amplifies the <= 2 ulp differences between
-    CUDA's and glibc's sinh/asinh in the x grid: there the bar is 5e-9 (DESIGN.md "Parity budget")."""
+    the bar -- also the stiff (4096, 64) shape (dt/dx^2 ~ 2000), which round 1 had to waive to 5e-9: the cause was the
+    rounding of the Moebius-composed pivots, cured by polishing them into the serial recurrence (DESIGN.md "Parity budget")."""
     from kwfd1d.synthetic import synthetic_options
 
     o = synthetic_options(64, 31, european_every=4, call_every=3)
@@ -483,16 +482,15 @@ def test_carry_truncation_modes(x, t, oracle):
     print("modes", x, t, [res[e][1] for e in (0, 1, 2)], "exact-vs-auto", maxdiff(res[0][0], res[2][0]),
           "vs oracle", [maxdiff(res[e][0], want) for e in (0, 1, 2)])
     assert maxdiff(res[0][0], res[2][0]) <= 1e-11 and maxdiff(res[1][0], res[2][0]) <= 1e-11
-    bar = TOL if t * 8 >= x else 5e-9
     for exact in (0, 1, 2):
-        assert maxdiff(res[exact][0], want) <= bar, (exact, maxdiff(res[exact][0], want))
+        assert maxdiff(res[exact][0], want) <= TOL, (exact, maxdiff(res[exact][0], want))
 
 
 def test_large_lambda_forces_exact_mode(oracle):
     """Few time steps on a fine grid (dt/dx^2 ~ 4000): the LU multipliers decay slowly (|a~| ~ 0.98 per
-    node), so the votes must keep every carry term (mode 0, general cross-warp rows with 16 warps).
-    At this lambda the reference's own arithmetic is sensitive to the last ulp of the grid
-    (DESIGN.md "Parity budget"), so the bar against the oracle is 2e-8 here, not 1e-9."""
+    node), so the votes must keep every carry term (mode 0, general cross-warp rows with 16 warps).  Round 1 waived
+    this shape to 2e-8 (measured 3.6e-9) and blamed libm; the oracle's own sensitivity to +-2 ulp of sinh / exp is 1e-10
+    here (tests/test_oracle.py) -- the cause was the scanned pivots, and with the polished ones the 1e-9 bar holds (2.3e-10)."""
     from kwfd1d.synthetic import synthetic_options
 
     o = synthetic_options(16, 32, call_every=2)
@@ -503,7 +501,7 @@ def test_large_lambda_forces_exact_mode(oracle):
     mc = p.info()["mode_count"]
     print("mode_count", mc, "max diff", maxdiff(got, want))
     assert mc[0] == 16
-    assert maxdiff(got, want) <= 2e-8
+    assert maxdiff(got, want) <= TOL
 
 
 def fp32_error(got, want):
