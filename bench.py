@@ -315,7 +315,7 @@ def measure(cx, pricer, opts_local, n_total, steps, warmup, strong, clocks=False
     for _ in range(min(steps, 5)):
         cx.flush.zero_()
         pricer.price_device(d_opts.data_ptr(), n, d_prices.data_ptr(), cx.sp)
-        torch.cuda.synchronize()
+        pricer.sync(cx.sp)
         kernel_ms.append(pricer.info()["last_kernel_ms"])
         if strong and cx.world > 1:
             g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -141,8 +141,12 @@ void kw_fd1d_destroy(kw_fd1d_handle* h);
 int kw_fd1d_price(kw_fd1d_handle* h, const kw_option* assets, size_t n, double* prices);
 
 /* Same computation with DEVICE-resident buffers (chain compression on the device when
- * cfg.compress == 1, otherwise one PDE per option), enqueued on `stream` (a cudaStream_t, may be 0) without synchronising.  Range errors are
- * reported by the next kw_fd1d_sync(). */
+ * cfg.compress == 1, otherwise one PDE per option), enqueued on `stream` (a cudaStream_t, may be 0) without
+ * synchronising.  Range errors are reported by the next kw_fd1d_sync(): several batches may be enqueued before one sync;
+ * the count and the smallest failing index (relative to its own batch) accumulate over them.
+ * ONE STREAM PER HANDLE: the handle's scratch (chain tables, set-up workspace, status block) is shared by its calls, so
+ * all kw_fd1d_price_device calls of a handle must be issued to the same stream (or be ordered by events); for concurrent
+ * streams use one handle per stream.  n <= 0xfffffff0. */
 int kw_fd1d_price_device(kw_fd1d_handle* h, const kw_option* d_assets, size_t n, double* d_prices,
                          void* stream);
 /* Waits for `stream`, then reports a pending range error (KW_FD1D_ERANGE) if any. */

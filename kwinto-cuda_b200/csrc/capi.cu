@@ -217,11 +217,16 @@ const RegVariant* find_variant(int xDim, int want_id, int prec)
     return first_fit;
 }
 
-__global__ void status_reset_kernel(unsigned int* status)
+// Before every march launch.  `keep_errors`: an earlier batch of this handle has not been synchronised yet
+// (kw_fd1d_price_device called several times before one kw_fd1d_sync): its range-error count and first failing
+// index must survive until the sync reads them, so only the per-launch fields are cleared.
+__global__ void status_reset_kernel(unsigned int* status, int keep_errors)
 {
-    status[0] = 0u;
-    status[1] = 0xffffffffu;
-    status[2] = status[3] = status[4] = status[5] = status[6] = status[7] = 0u;
+    if (!keep_errors) {
+        status[0] = 0u;
+        status[1] = 0xffffffffu;
+        status[2] = status[3] = status[4] = status[5] = status[6] = status[7] = 0u;
+    }
     status[8] = 0u;  // work counter of the independent-warp kernels
 }
 
@@ -363,6 +368,7 @@ struct kw_fd1d_handle {
     // Multi-device handle (kw_fd1d_create_multi / cfg.n_devices > 1): this object only coordinates; every entry
     // of `shards` is a complete single-device handle (its own stream, device buffers, pinned staging) and prices a
     // contiguous block of the batch on its device.  Empty for a single-device handle.
+    bool unsynced = false;  // a batch was enqueued and its status not read yet (check_status clears)
     std::vector<kw_fd1d_handle*> shards;
     uint32_t shards_used = 0;  // shards the last call spread the batch over
     double last_wall_ms = 0.;  // multi-device: wall time of the last price call (max over shards is in last_kernel_ms)
@@ -400,7 +406,8 @@ int launch_batch(kw_fd1d_handle* h, Fd1dBatch B, cudaStream_t st)
     for (int i = 0; i < 4; ++i) B.opq_lim[i] = INT32_MAX;
     B.opq_zero = 0;
     B.work_counter = B.status + 8;
-    status_reset_kernel<<<1, 1, 0, st>>>(B.status);
+    status_reset_kernel<<<1, 1, 0, st>>>(B.status, h->unsynced ? 1 : 0);
+    h->unsynced = true;
     h->launches += 1;
     h->last_n_pde = B.n_pde;
     if (h->layout == KW_FD1D_LAYOUT_REG) {
@@ -638,6 +645,7 @@ int check_status(kw_fd1d_handle* h, cudaStream_t st, const kw_option* host_asset
     KW_CUDA(h, h->h_status.reserve(8));
     KW_CUDA(h, cudaMemcpyAsync(h->h_status.p, h->d_status.p, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     KW_CUDA(h, cudaStreamSynchronize(st));
+    h->unsynced = false;
     for (int i = 0; i < 6; ++i) h->mode_count[i] = h->h_status.p[2 + i];
     if (h->dev_compressed) {
         // the PDE count stayed on the device; it is the sum of the per-mode counters of the march

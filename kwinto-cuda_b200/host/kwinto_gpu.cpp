@@ -15,6 +15,12 @@
 #include <vector>
 
 #include "kw/kwPortfolio.h"
+#ifdef KW_WITH_REFERENCE
+// Built inside the reference tree (make kwinto-gpu-ref: the reference's own pricer sources are compiled into THIS
+// driver binary, never into libkwfd1d.so): the --cpu64 arm of the historic bench is the reference's Fd1d_Pricer on
+// its thread pool (src/Pricer/kwPricerFactory.h:15-41, mode "FD1D").
+#include "Pricer/kwPricerFactory.h"
+#endif
 
 using namespace kw;
 
@@ -43,7 +49,9 @@ Options:
     -b <num>        Options per batch [default: 32768]
     -n <num>        Number of batches [default: 4]
     --gpu32         Benchmark the fp32 march
-    --gpu64         Benchmark the fp64 march (default when neither is given)
+    --gpu64         Benchmark the fp64 march (default when no arm is given)
+    --cpu64         Benchmark the reference's CPU Fd1d pricer (thread pool, fp64); needs the kwinto-gpu-ref build
+    --cpu32         Historic fp32 CPU arm (log/z800_1024_32768.log:42-48): the reference's source has no fp32 pricer any more
     --call          Use calls only
     --put           Use puts only
 
@@ -57,7 +65,8 @@ struct Args {
                                            {"-p", "FD1D-BS-GPU"}, {"-t", "512"},      {"-x", "512"},
                                            {"--precision", "f64"}, {"--device", "0"}, {"-b", "32768"},
                                            {"-n", "4"}};
-    std::map<std::string, bool> flag{{"-v", false}, {"--gpu32", false}, {"--gpu64", false}, {"--call", false}, {"--put", false}};
+    std::map<std::string, bool> flag{{"-v", false},     {"--gpu32", false}, {"--gpu64", false}, {"--cpu32", false},
+                                     {"--cpu64", false}, {"--call", false},  {"--put", false}};
 };
 
 static Error parseArgs(int argc, char** argv, Args& a)
@@ -194,15 +203,35 @@ static Error cmdBench(const Args& a)
     std::cout << "    Batch size : " << batch << std::endl;
     std::cout << std::endl;
 
-    std::vector<std::string> precisions;
-    if (a.flag.at("--gpu32")) precisions.push_back("f32");
-    if (a.flag.at("--gpu64") || precisions.empty()) precisions.push_back("f64");
+    // the arms of the historic bench, in its order: cpu32, cpu64, gpu32, gpu64 (log/z800_1024_32768.log:42-110)
+    std::vector<std::string> arms;
+    if (a.flag.at("--cpu32")) arms.push_back("cpu32");
+    if (a.flag.at("--cpu64")) arms.push_back("cpu64");
+    if (a.flag.at("--gpu32")) arms.push_back("f32");
+    if (a.flag.at("--gpu64") || arms.empty()) arms.push_back("f64");
 
-    for (const auto& prec : precisions) {
-        config.set("FD1D.GPU.PRECISION", prec);
+    for (const auto& prec : arms) {
         sPtr<Pricer> pricer;
-        if (auto err = GpuPricerFactory::create(config, pricer); !err.empty()) return "cmdBench: " + err;
-        const std::string label = std::string("Fd1dGpu_Pricer<") + (prec == "f32" ? "float" : "double") + ">::price";
+        std::string label;
+        if (prec == "cpu32") {
+            std::cout << "Benchmark for Fd1d_Pricer<float>::price\n    not available: the reference's source has no "
+                         "single-precision CPU pricer any more (src/Math/kwFd1d.h is f64 only)\n" << std::endl;
+            continue;
+        } else if (prec == "cpu64") {
+#ifdef KW_WITH_REFERENCE
+            Config cpu = config;
+            cpu.set("PRICER", std::string(a.opt.at("-p") == "FD1D-BS" || a.opt.at("-p") == "FD1D-BS-GPU" ? "FD1D-BS" : "FD1D"));
+            if (auto err = PricerFactory::create(cpu, pricer); !err.empty()) return "cmdBench: " + err;
+            label = "Fd1d_Pricer<double>::price";
+#else
+            return "cmdBench: --cpu64 needs the kwinto-gpu-ref build (the reference's pricer sources compiled into the driver: "
+                   "make -C kwinto-cuda_b200/host ref)";
+#endif
+        } else {
+            config.set("FD1D.GPU.PRECISION", prec);
+            if (auto err = GpuPricerFactory::create(config, pricer); !err.empty()) return "cmdBench: " + err;
+            label = std::string("Fd1dGpu_Pricer<") + (prec == "f32" ? "float" : "double") + ">::price";
+        }
 
         // batches wrap around the portfolio when it is smaller than count * batch
         std::vector<Option> in((size_t)batch);

@@ -632,3 +632,32 @@ def test_signed_zero_dividend_is_one_chain(compress, oracle):
     assert err == "" and p.info()["last_n_pde"] == 1, p.info()["last_n_pde"]
     want, oerr = oracle.fd1d(o, 128, 512)
     assert oerr == "" and maxdiff(got, want) <= TOL
+
+
+@pytest.mark.gpu
+def test_range_error_survives_later_batches_until_sync():
+    """kw_fd1d_price_device may be called several times before one kw_fd1d_sync (bench.py does): a range error of an
+    earlier batch must still be reported by that sync (round 1 reset the status block at every enqueue)."""
+    import torch
+
+    from kwfd1d.synthetic import synthetic_options
+
+    good = synthetic_options(1500, 5)
+    bad = good.copy()
+    bad["s"][700] = 1e300
+    p = make_pricer(64, 1024)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def enqueue(o):
+        d_o = torch.from_numpy(o.view(np.uint8).reshape(-1).copy()).cuda()
+        d_p = torch.empty(o.shape[0], dtype=torch.float64, device="cuda")
+        assert p.price_device(d_o.data_ptr(), o.shape[0], d_p.data_ptr(), stream) == ""
+        return d_o, d_p
+
+    keep = [enqueue(bad), enqueue(good), enqueue(good)]
+    err = p.sync(stream)
+    assert "not in range" in err, err
+    assert torch.isnan(keep[0][1][700]) and torch.isfinite(keep[1][1]).all()
+    # the handle recovers: a clean batch after the sync reports no error
+    keep.append(enqueue(good))
+    assert p.sync(stream) == ""

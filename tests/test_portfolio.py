@@ -149,3 +149,26 @@ def test_python_portfolio_price(csv_files):
     assert st["total"] == 4543 and abs(st["rmse"] - REF_STATS_FD1D["rmse"]) <= 1e-6 * REF_STATS_FD1D["rmse"]
     err, _ = p.price(kwfd1d.Config(PRICER="NOPE"))
     assert err == "Portfolio::price : PricerFactory: Unknown PRICER = NOPE"
+
+
+def test_cli_bench_cpu_arms(csv_files):
+    """The --cpu64 / --cpu32 arms of the historic bench (log/z800_1024_32768.log:42-78, Makefile:5).  The CPU arm is the
+    reference's own Fd1d_Pricer, compiled from the reference tree into the DRIVER binary kwinto-gpu-ref (never into
+    libkwfd1d.so), so it runs without a GPU; the plain driver refuses the flag."""
+    plain, _, _ = csv_files
+    r = subprocess.run([CLI, "bench", "--cpu64", "-b", "64", "-n", "2", "-x", "64", "-t", "64", plain],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 1 and "kwinto-gpu-ref" in r.stderr
+    ref_cli = CLI + "-ref"
+    if not os.path.exists(ref_cli):
+        pytest.skip("kwinto-gpu-ref is built only where the reference tree is mounted")
+    r = subprocess.run([ref_cli, "bench", "--cpu32", "--cpu64", "-p", "FD1D", "--put", "-b", "256", "-n", "2", "-x", "128",
+                        "-t", "128", plain], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = r.stdout
+    for needle in ("Batch count: 2", "Batch size : 256", "Benchmark for Fd1d_Pricer<float>::price", "not available",
+                   "Benchmark for Fd1d_Pricer<double>::price", "funCall : 2 times", "options/s :",
+                   "Errors for Fd1d_Pricer<double>::price", "RRMSE :"):
+        assert needle in out, (needle, out)
+    rrmse = float(re.search(r"RRMSE : (\S+)", out).group(1))
+    assert 0 < rrmse < 5e-2  # 128 x 128 grid against the QuantLib reference prices
