@@ -147,6 +147,8 @@ const RegVariant g_variants[] = {
     KW_VARIANT_F32(1301, 8, 256, 2),
     KW_VARIANT_F32(1401, 8, 512, 1),
 #ifdef KW_EXPERIMENTS
+    {239, KW_FD1D_F64, 8, 128, 2, false, false, fd1d_iw_kernel<4, 2, false, true>, IwSmem<4>::bytes(), 256, 4},  // 237 with half-chunk
+                                               // lookahead (four dependent chains per warp, +16 DFMAs per step): 28.4 vs 24.1 ms
     KW_VARIANT(2, 8, 32, 16, true, true),
     KW_VARIANT(102, 8, 64, 8, true, true),
     KW_VARIANT(103, 8, 64, 6, true, false),

@@ -31,7 +31,8 @@ __device__ __noinline__ double payoff_node_ni(bool put, double x) { return payof
 template <int NCH>
 struct IwSmem {
     static constexpr int N = 8 * NCH * 32;  // nodes per PDE tile
-    static constexpr int SCR = 28 * 32;     // set-up scratch per warp: chunk maps [16][32], chunk scalars [12][32]
+    static constexpr int SCR = 40 * 32;     // scratch per warp [row][lane]: half-chunk constants [5 * 4], carried half-chunk
+                                            // values e_3, l_4 [2 * 4], chunk scalars of the set-up [12]
     // doubles per warp: final v of its PDE [N] (the payoff stage during set-up) | set-up scratch [SCR]
     static constexpr size_t bytes() { return sizeof(double) * (size_t)(4 * (N + SCR)); }
 };
@@ -42,7 +43,17 @@ struct IwSmem {
 // the warp marches its chain as given, prices into B.prices, re-creates the payoff and marches the European copy
 // (no floor loads, compares or selects) into B.prices_eu.  A chain given as European is marched once and priced into
 // both arrays.  capi.cu adds the closed form (bs_combine_kernel).
-template <int NCH, int MINB, bool BS = false>
+// D4: every 8-node sweep is split into two 4-node half-chains that run side by side.  The second half does not wait for
+// the first: its entry value comes from a one- or two-DFMA lookahead through precomputed half-chunk products and the
+// half-chunk results of the previous local sweeps,
+//     forward   y_3* = e_3 + P_lo Yin              (e_3: lo half's local forward value, P_lo = a_0 a_1 a_2 a_3)
+//     backward  u_4* = l_4 + R_hi y_3* + Q_hi Uin  (l_4: hi half's local backward value, R_hi, Q_hi = g_4 ... g_7)
+// and the local sweeps are two 3-deep Horner halves combined by  e_c = e_hi + P_hi e_3,  f_c = l_lo + Q_lo (l_4 + R_hi e_3).
+// 16 more DFMAs per step (186 instead of 170) for FOUR dependent chains per warp in every sweep phase instead of two and a
+// dependent depth of 20 instead of 30 DFMAs per pair: the march is bound by the 8-cycle dependent-issue latency of the chains
+// two warps can keep in flight, not by the FP64 pipe.  Five constants per chunk and the two carried
+// half-chunk values live in the warp's shared scratch ([row][lane], one LDS / STS per use).
+template <int NCH, int MINB, bool BS = false, bool D4 = false>
 __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
 {
     static_assert(NCH == 4 || NCH == 2, "4 chunks per lane (512 < x <= 1024) or 2 (256 < x <= 512)");
@@ -89,7 +100,8 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
         {
             const int j0 = lane * NODES;
             double* s_v = vfin;            // [NODES][32] payoff, until the registers take it
-            double* s_k = scr + 16 * 32;   // [3 * NCH][32] chunk scalars
+            double* s_k = scr + 28 * 32;   // [3 * NCH][32] chunk scalars
+            double* s_h = scr;             // [5 * NCH][32] half-chunk constants P_lo, P_hi, Q_lo, Q_hi, R_hi (D4)
             // ---- grid, payoff, projection floor, rows of B (parked in tensor memory)
             double bu_carry = 0.;
             {
@@ -272,6 +284,18 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
                     s_k[(3 * c + 0) * 32 + lane] = Pp[7];
                     s_k[(3 * c + 1) * 32 + lane] = Q0;
                     s_k[(3 * c + 2) * 32 + lane] = R0;
+                    if constexpr (D4) {
+                        const double Ph4 = a[4], Ph5 = a[5] * Ph4, Ph6 = a[6] * Ph5, Ph7 = a[7] * Ph6;
+                        double Rh = Ph7;  // response of the hi half's first backward value to its incoming forward value
+                        Rh = fma(g[6], Rh, Ph6);
+                        Rh = fma(g[5], Rh, Ph5);
+                        Rh = fma(g[4], Rh, Ph4);
+                        s_h[(5 * c + 0) * 32 + lane] = Pp[3];                       // P_lo = a_0 a_1 a_2 a_3
+                        s_h[(5 * c + 1) * 32 + lane] = Ph7;                         // P_hi = a_4 a_5 a_6 a_7
+                        s_h[(5 * c + 2) * 32 + lane] = ((g[0] * g[1]) * g[2]) * g[3];  // Q_lo
+                        s_h[(5 * c + 3) * 32 + lane] = ((g[7] * g[6]) * g[5]) * g[4];  // Q_hi
+                        s_h[(5 * c + 4) * 32 + lane] = Rh;
+                    }
 #pragma unroll
                     for (int i = 0; i < 8; ++i) bmax = fmax(bmax, D[i] != 0. ? fabs(2. / D[i]) : 1.);
                     ib_prev = ib[7];
@@ -350,21 +374,58 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
             constexpr int LEV = decltype(lev_c)::value;
             constexpr bool EURO = decltype(euro_c)::value;  // European copy: no floor, no compare
             double e[NCH], f[NCH];
+            // D4: half-chunk constants and carried half-chunk values in the warp's scratch, [row][lane]
+            const uint32_t a_h = smem_addr(scr + lane);
+            auto hP_lo = [&](int c) { return lds_f64(a_h + (5 * c + 0) * 256); };
+            auto hP_hi = [&](int c) { return lds_f64(a_h + (5 * c + 1) * 256); };
+            auto hQ_lo = [&](int c) { return lds_f64(a_h + (5 * c + 2) * 256); };
+            auto hQ_hi = [&](int c) { return lds_f64(a_h + (5 * c + 3) * 256); };
+            auto hR_hi = [&](int c) { return lds_f64(a_h + (5 * c + 4) * 256); };
+            auto ld_e3 = [&](int c) { return lds_f64(a_h + (20 + c) * 256); };
+            auto ld_l4 = [&](int c) { return lds_f64(a_h + (24 + c) * 256); };
+            auto st_e3 = [&](int c, double v) { sts_f64(a_h + (20 + c) * 256, v); };
+            auto st_l4 = [&](int c, double v) { sts_f64(a_h + (24 + c) * 256, v); };
+            // local sweeps of chunk c from zero (next step's aggregates): e = last forward value, f = first backward value
+            auto local_chunk = [&](int c, const double (&a8)[8], const double (&g8)[8]) {
+                if constexpr (!D4) {
+                    double y[8];
+                    y[0] = vr[8 * c];
+#pragma unroll
+                    for (int i = 1; i < 8; ++i) y[i] = fma(a8[i], y[i - 1], vr[8 * c + i]);
+                    e[c] = y[7];
+                    double u = y[7];
+#pragma unroll
+                    for (int i = 6; i >= 0; --i) u = fma(g8[i], u, y[i]);
+                    f[c] = u;
+                } else {
+                    double y[8];
+                    y[0] = vr[8 * c];
+                    y[4] = vr[8 * c + 4];
+#pragma unroll
+                    for (int i = 1; i < 4; ++i) {
+                        y[i] = fma(a8[i], y[i - 1], vr[8 * c + i]);
+                        y[4 + i] = fma(a8[4 + i], y[3 + i], vr[8 * c + 4 + i]);
+                    }
+                    const double e3 = y[3];
+                    e[c] = fma(hP_hi(c), e3, y[7]);
+                    double ul = y[3], uh = y[7];
+#pragma unroll
+                    for (int i = 2; i >= 0; --i) {
+                        ul = fma(g8[i], ul, y[i]);
+                        uh = fma(g8[4 + i], uh, y[4 + i]);
+                    }
+                    f[c] = fma(hQ_lo(c), fma(hR_hi(c), e3, uh), ul);
+                    st_e3(c, e3);
+                    st_l4(c, uh);
+                }
+            };
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
                 double a8[8], g8[8];
                 tmem::ld8(tbase + T_A + 16 * c, a8);
                 tmem::ld8(tbase + T_G + 16 * c, g8);
                 tmem::wait_ld_dep(a8, g8);
-                double y[8];
-                y[0] = vr[8 * c];
-#pragma unroll
-                for (int i = 1; i < 8; ++i) y[i] = fma(a8[i], y[i - 1], vr[8 * c + i]);
-                e[c] = y[7];
-                double u = y[7];
-#pragma unroll
-                for (int i = 6; i >= 0; --i) u = fma(g8[i], u, y[i]);
-                f[c] = u;
+                local_chunk(c, a8, g8);
             }
             double Yin[NCH], Uin[NCH];
             // ---- the scans of one step: lane aggregates, Kogge-Stone over the lanes, chunk-entry / -exit values
@@ -402,22 +463,39 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
                 for (int c = NCH - 2; c >= 0; --c) Uin[c] = fma(kG(c + 1), Uin[c + 1], f[c + 1]);
             };
             // ---- true forward sweeps of the chunk pair (cA, cA + 1) from Yin
-            auto fwd_pair = [&](int cA, double (&yA)[8], double (&yB)[8]) {
+            // (D4: y3[0], y3[1] = the lookahead values y_3* of the two chunks, needed again by the backward lookahead)
+            auto fwd_pair = [&](int cA, double (&yA)[8], double (&yB)[8], double (&y3)[2]) {
                 const int cB = cA + 1;
                 double aA[8], aB[8];
                 tmem::ld8(tbase + T_A + 16 * cA, aA);
                 tmem::ld8(tbase + T_A + 16 * cB, aB);
                 tmem::hot_wait(aA, aB);
-                yA[0] = fma(aA[0], Yin[cA], vr[8 * cA]);
-                yB[0] = fma(aB[0], Yin[cB], vr[8 * cB]);
+                if constexpr (!D4) {
+                    yA[0] = fma(aA[0], Yin[cA], vr[8 * cA]);
+                    yB[0] = fma(aB[0], Yin[cB], vr[8 * cB]);
 #pragma unroll
-                for (int i = 1; i < 8; ++i) {
-                    yA[i] = fma(aA[i], yA[i - 1], vr[8 * cA + i]);
-                    yB[i] = fma(aB[i], yB[i - 1], vr[8 * cB + i]);
+                    for (int i = 1; i < 8; ++i) {
+                        yA[i] = fma(aA[i], yA[i - 1], vr[8 * cA + i]);
+                        yB[i] = fma(aB[i], yB[i - 1], vr[8 * cB + i]);
+                    }
+                } else {
+                    y3[0] = fma(hP_lo(cA), Yin[cA], ld_e3(cA));
+                    y3[1] = fma(hP_lo(cB), Yin[cB], ld_e3(cB));
+                    yA[0] = fma(aA[0], Yin[cA], vr[8 * cA]);
+                    yB[0] = fma(aB[0], Yin[cB], vr[8 * cB]);
+                    yA[4] = fma(aA[4], y3[0], vr[8 * cA + 4]);
+                    yB[4] = fma(aB[4], y3[1], vr[8 * cB + 4]);
+#pragma unroll
+                    for (int i = 1; i < 4; ++i) {
+                        yA[i] = fma(aA[i], yA[i - 1], vr[8 * cA + i]);
+                        yB[i] = fma(aB[i], yB[i - 1], vr[8 * cB + i]);
+                        yA[4 + i] = fma(aA[4 + i], yA[3 + i], vr[8 * cA + 4 + i]);
+                        yB[4 + i] = fma(aB[4 + i], yB[3 + i], vr[8 * cB + 4 + i]);
+                    }
                 }
             };
             // ---- true backward sweeps from Uin, projection, next step's local sweeps (a~, g~ loaded again)
-            auto back_pair = [&](int cA, double (&yA)[8], double (&yB)[8]) {
+            auto back_pair = [&](int cA, double (&yA)[8], double (&yB)[8], const double (&y3)[2]) {
                 const int cB = cA + 1;
                 double gA[8], gB[8], dA[8], dB[8], pA[8], pB[8];
                 tmem::ld8(tbase + T_G + 16 * cA, gA);
@@ -433,9 +511,7 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
                     tmem::hot_wait(gA, gB);
                     tmem::hot_wait(dA, dB);
                 }
-                double uA = Uin[cA], uB = Uin[cB];
-#pragma unroll
-                for (int i = 7; i >= 0; --i) {
+                auto node = [&](int i, double& uA, double& uB) {
                     uA = fma(gA[i], uA, yA[i]);
                     uB = fma(gB[i], uB, yB[i]);
                     const double rA = fma(dA[i], uA, -vr[8 * cA + i]);
@@ -447,6 +523,20 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
                         vr[8 * cA + i] = max_like_std(rA, pA[i]);
                         vr[8 * cB + i] = max_like_std(rB, pB[i]);
                     }
+                };
+                if constexpr (!D4) {
+                    double uA = Uin[cA], uB = Uin[cB];
+#pragma unroll
+                    for (int i = 7; i >= 0; --i) node(i, uA, uB);
+                } else {
+                    double uhA = Uin[cA], uhB = Uin[cB];
+                    double ulA = fma(hQ_hi(cA), Uin[cA], fma(hR_hi(cA), y3[0], ld_l4(cA)));  // u_4* of chunk A
+                    double ulB = fma(hQ_hi(cB), Uin[cB], fma(hR_hi(cB), y3[1], ld_l4(cB)));
+#pragma unroll
+                    for (int i = 3; i >= 0; --i) {
+                        node(4 + i, uhA, uhB);
+                        node(i, ulA, ulB);
+                    }
                 }
                 double aA[8], aB[8];
                 tmem::ld8(tbase2 + T_A + 16 * cA, aA);
@@ -455,42 +545,72 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
                 tmem::ld8(tbase2 + T_G + 16 * cB, gB);
                 tmem::hot_wait(aA, aB);
                 tmem::hot_wait(gA, gB);
-                yA[0] = vr[8 * cA];
-                yB[0] = vr[8 * cB];
+                if constexpr (!D4) {
+                    yA[0] = vr[8 * cA];
+                    yB[0] = vr[8 * cB];
 #pragma unroll
-                for (int i = 1; i < 8; ++i) {
-                    yA[i] = fma(aA[i], yA[i - 1], vr[8 * cA + i]);
-                    yB[i] = fma(aB[i], yB[i - 1], vr[8 * cB + i]);
-                }
-                e[cA] = yA[7];
-                e[cB] = yB[7];
-                uA = yA[7];
-                uB = yB[7];
+                    for (int i = 1; i < 8; ++i) {
+                        yA[i] = fma(aA[i], yA[i - 1], vr[8 * cA + i]);
+                        yB[i] = fma(aB[i], yB[i - 1], vr[8 * cB + i]);
+                    }
+                    e[cA] = yA[7];
+                    e[cB] = yB[7];
+                    double uA = yA[7], uB = yB[7];
 #pragma unroll
-                for (int i = 6; i >= 0; --i) {
-                    uA = fma(gA[i], uA, yA[i]);
-                    uB = fma(gB[i], uB, yB[i]);
+                    for (int i = 6; i >= 0; --i) {
+                        uA = fma(gA[i], uA, yA[i]);
+                        uB = fma(gB[i], uB, yB[i]);
+                    }
+                    f[cA] = uA;
+                    f[cB] = uB;
+                } else {
+                    // four 3-deep Horner halves forward, four backward, combined through the half-chunk products
+                    yA[0] = vr[8 * cA];
+                    yB[0] = vr[8 * cB];
+                    yA[4] = vr[8 * cA + 4];
+                    yB[4] = vr[8 * cB + 4];
+#pragma unroll
+                    for (int i = 1; i < 4; ++i) {
+                        yA[i] = fma(aA[i], yA[i - 1], vr[8 * cA + i]);
+                        yB[i] = fma(aB[i], yB[i - 1], vr[8 * cB + i]);
+                        yA[4 + i] = fma(aA[4 + i], yA[3 + i], vr[8 * cA + 4 + i]);
+                        yB[4 + i] = fma(aB[4 + i], yB[3 + i], vr[8 * cB + 4 + i]);
+                    }
+                    e[cA] = fma(hP_hi(cA), yA[3], yA[7]);
+                    e[cB] = fma(hP_hi(cB), yB[3], yB[7]);
+                    double ulA = yA[3], ulB = yB[3], uhA = yA[7], uhB = yB[7];
+#pragma unroll
+                    for (int i = 2; i >= 0; --i) {
+                        ulA = fma(gA[i], ulA, yA[i]);
+                        ulB = fma(gB[i], ulB, yB[i]);
+                        uhA = fma(gA[4 + i], uhA, yA[4 + i]);
+                        uhB = fma(gB[4 + i], uhB, yB[4 + i]);
+                    }
+                    f[cA] = fma(hQ_lo(cA), fma(hR_hi(cA), yA[3], uhA), ulA);
+                    f[cB] = fma(hQ_lo(cB), fma(hR_hi(cB), yB[3], uhB), ulB);
+                    st_e3(cA, yA[3]);
+                    st_e3(cB, yB[3]);
+                    st_l4(cA, uhA);
+                    st_l4(cB, uhB);
                 }
-                f[cA] = uA;
-                f[cB] = uB;
             };
             // Rotated loop.  Block X: pair 0 backwards (its forward sweeps were done at the end of the previous
             // iteration).  Block Z: the other pair in full, then the NEXT step's scans with pair 0's forward sweeps
             // behind them -- the shuffles' latency hides behind the sweeps of the same basic block.
-            double y0A[8], y0B[8];
+            double y0A[8], y0B[8], y30[2] = {0., 0.};
             scan();
-            fwd_pair(0, y0A, y0B);
+            fwd_pair(0, y0A, y0B, y30);
             for (int step = 0; step < nsteps; ++step) {
-                if (step < B.opq_lim[0]) back_pair(0, y0A, y0B);  // always true: basic-block boundary
+                if (step < B.opq_lim[0]) back_pair(0, y0A, y0B, y30);  // always true: basic-block boundary
                 if (step < B.opq_lim[1]) {
 #pragma unroll
                     for (int h = 2; h < NCH; h += 2) {
-                        double yA[8], yB[8];
-                        fwd_pair(h, yA, yB);
-                        back_pair(h, yA, yB);
+                        double yA[8], yB[8], y3[2] = {0., 0.};
+                        fwd_pair(h, yA, yB, y3);
+                        back_pair(h, yA, yB, y3);
                     }
                     scan();
-                    fwd_pair(0, y0A, y0B);  // after the last step: computed and dropped
+                    fwd_pair(0, y0A, y0B, y30);  // after the last step: computed and dropped
                 }
             }
             tmem::wait_ld();  // nothing in flight when the arrays are rewritten

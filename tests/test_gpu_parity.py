@@ -174,7 +174,7 @@ def test_layouts_agree_with_reference(layout):
         assert maxdiff(got, g[k + "/fd1d"]) <= TOL, (layout, k)
 
 
-@pytest.mark.parametrize("variant", [201, 202, 203, 204, 205, 211, 213, 221, 222, 231, 232, 233, 234, 235, 236, 237, 241, 242])
+@pytest.mark.parametrize("variant", [201, 202, 203, 204, 205, 211, 213, 221, 222, 231, 232, 233, 234, 235, 236, 237, 239, 241, 242])
 def test_all_1024_variants(variant):
     g, _ = synthetic_cases()
     p = make_pricer(1024, 1024, **{"FD1D.GPU.VARIANT": variant})
@@ -183,7 +183,7 @@ def test_all_1024_variants(variant):
     assert err == "" and maxdiff(got, g["mix_1024/fd1d"]) <= TOL
 
 
-@pytest.mark.parametrize("variant,x", [(1, 256), (2, 256), (101, 512), (102, 512), (103, 512), (133, 512), (133, 300), (136, 512), (136, 300), (137, 512), (137, 300), (237, 1024), (237, 700), (301, 2048),
+@pytest.mark.parametrize("variant,x", [(1, 256), (2, 256), (101, 512), (102, 512), (103, 512), (133, 512), (133, 300), (136, 512), (136, 300), (137, 512), (137, 300), (237, 1024), (237, 700), (239, 1024), (239, 700), (301, 2048),
                                         (302, 2048), (401, 4096), (402, 4096), (331, 2048), (331, 1100), (431, 4096), (431, 3000), (336, 2048), (336, 1100), (436, 4096), (436, 3000)])
 def test_other_variants(variant, x, oracle):
     from kwfd1d.synthetic import synthetic_options
