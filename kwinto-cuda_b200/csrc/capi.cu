@@ -396,10 +396,17 @@ int fail(kw_fd1d_handle* h, int code, const std::string& msg)
 int prepare_variant(kw_fd1d_handle* h, const RegVariant* var, const cudaDeviceProp& prop, int& ctas_per_sm, int& regs);
 const RegVariant* find_small_variant(int xDim, int prec);
 
+// Layout A streams 7 arrays of xDim doubles per PDE through HBM and has ONE thread per PDE: it needs hundreds of
+// thousands of PDEs in flight to hide the latency of its dependent sweeps, so a chunk is as many PDEs as fit half of
+// the free device memory (180 GB hold 1.6 M PDEs at x = 1024), not a fixed 65536.
 size_t soa_chunk(const kw_fd1d_handle* h, size_t n_pde)
 {
-    (void)h;
-    return std::min<size_t>(n_pde, 65536);
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = (size_t)8 << 30;
+    const size_t per_pde = 7 * sizeof(double) * (size_t)h->cfg.x_grid_size;
+    size_t fit = std::max<size_t>(4096, (free_b / 2 + h->d_soa.cap * sizeof(double)) / per_pde);
+    if (const char* e = getenv("KW_FD1D_SOA_CHUNK")) fit = std::max<size_t>(128, (size_t)atoll(e));
+    return std::min<size_t>(n_pde, fit);
 }
 
 // enqueue the solve of `n_pde` PDEs on `st`; all pointers are device pointers
