@@ -285,6 +285,7 @@ __device__ __forceinline__ void setup_lu(const Fd1dBatch& B, const PdeScalars& s
         // the serial recurrence of src/Math/kwMath.cpp:30-38, bit for bit.
         {
             double pin = s_bin[k];
+            __syncthreads();  // every thread holds its first guess before a neighbour overwrites it
 #pragma unroll 1
             for (int sweep = 0; sweep < P + 2; ++sweep) {
                 double prev = pin;
