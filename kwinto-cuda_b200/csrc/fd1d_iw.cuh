@@ -438,10 +438,11 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
                     const double o = __shfl_up_sync(FULL, S, 1 << d);
                     S = fma(kAf(d), o, S);
                 }
-                {
-                    const double o = __shfl_up_sync(FULL, S, 1);
-                    Yin[0] = lane ? o : 0.;
-                }
+                // Lane 0 has no predecessor: __shfl_up hands it its own (finite) S back.  No select is needed -- whatever
+                // Yin[0] is there, it is only ever multiplied by a~ of the grid's first node, A_0 or R0_0 of lane 0's first
+                // chunk, all exactly 0 (a~_0 = -bl_0 / beta_{-1} with 1/beta_{-1} = 0).  Likewise Uin of lane 31's last chunk
+                // below (g~ of the last node is 0).
+                Yin[0] = __shfl_up_sync(FULL, S, 1);
 #pragma unroll
                 for (int c = 1; c < NCH; ++c) Yin[c] = fma(kA(c - 1), Yin[c - 1], e[c - 1]);
                 // backward: chunk-start values with the true forward carry, scan, chunk-exit values
@@ -455,10 +456,7 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
                     const double o = __shfl_down_sync(FULL, T, 1 << d);
                     T = fma(kGb(d), o, T);
                 }
-                {
-                    const double o = __shfl_down_sync(FULL, T, 1);
-                    Uin[NCH - 1] = lane < 31 ? o : 0.;
-                }
+                Uin[NCH - 1] = __shfl_down_sync(FULL, T, 1);
 #pragma unroll
                 for (int c = NCH - 2; c >= 0; --c) Uin[c] = fma(kG(c + 1), Uin[c + 1], f[c + 1]);
             };

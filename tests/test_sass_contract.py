@@ -34,7 +34,7 @@ def test_every_ldtm_is_scoreboarded_and_waited_for(contract):
     assert problems == [], "\n".join(problems[:20])
     by_name = {name: (n_ldtm, n_sttm, march) for name, _, n_ldtm, n_sttm, march in report}
     # the kernels that keep a~, g~, D, p in tensor memory really do (SASS: LDTM / STTM), and their march loops were found
-    for key, min_loops in (("fd1d_iw_kernelILi4ELi2ELb0E", 5), ("fd1d_iw_kernelILi4ELi2ELb1E", 10), ("fd1d_wide_kernelILi4", 5),
+    for key, min_loops in (("fd1d_iw_kernelILi4ELi2ELb0ELb0E", 5), ("fd1d_iw_kernelILi4ELi2ELb1ELb0E", 10), ("fd1d_wide_kernelILi4", 5),
                            ("fd1d_wide_kernelILi2", 5), ("fd1d_warpf_kernelILi4", 5)):
         hits = [v for k, v in by_name.items() if key in k]
         assert hits, key
@@ -42,7 +42,7 @@ def test_every_ldtm_is_scoreboarded_and_waited_for(contract):
             assert n_ldtm >= 16 and n_sttm >= 4, (key, n_ldtm, n_sttm)
             assert len(march) >= min_loops, (key, len(march))
     # the headline kernel: every march loop has 24 LDTM per step (a~, g~, D, p + a~, g~ again) and at most 16 moves
-    (n_ldtm, n_sttm, march), = [v for k, v in by_name.items() if "fd1d_iw_kernelILi4ELi2ELb0E" in k]
+    (n_ldtm, n_sttm, march), = [v for k, v in by_name.items() if "fd1d_iw_kernelILi4ELi2ELb0ELb0E" in k]
     steps = [m for a, b, m in march if m["LDTM"] == 24 and m["DSETP"] == 32]  # the five level-specialised march steps
     assert len(steps) == 5
     for mix in steps:
@@ -55,9 +55,9 @@ def test_the_checker_sees_a_missing_wait(contract):
     checker must object."""
     import subprocess
 
-    sc, _, _ = contract
-    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN6kwfd1d14fd1d_iw_kernelILi4ELi2ELb0EEEvNS_9Fd1dBatchE", LIB],
-                          capture_output=True, text=True, check=True).stdout
+    sc, report, _ = contract
+    (mangled,) = [name for name, *_ in report if "fd1d_iw_kernelILi4ELi2ELb0ELb0E" in name]  # the headline kernel
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", mangled, LIB], capture_output=True, text=True, check=True).stdout
     (name, body), = sc.split_functions(sass).items()
     code = sc.parse_function(body)
     assert sc.check_function(name, code)[2] == []
