@@ -465,8 +465,7 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
             auto fwd_pair = [&](int cA, double (&yA)[8], double (&yB)[8], double (&y3)[2]) {
                 const int cB = cA + 1;
                 double aA[8], aB[8];
-                tmem::ld8(tbase + T_A + 16 * cA, aA);
-                tmem::ld8(tbase + T_A + 16 * cB, aB);
+                tmem::ld16(tbase + T_A + 16 * cA, aA, aB);
                 tmem::hot_wait(aA, aB);
                 if constexpr (!D4) {
                     yA[0] = fma(aA[0], Yin[cA], vr[8 * cA]);
@@ -496,13 +495,10 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
             auto back_pair = [&](int cA, double (&yA)[8], double (&yB)[8], const double (&y3)[2]) {
                 const int cB = cA + 1;
                 double gA[8], gB[8], dA[8], dB[8], pA[8], pB[8];
-                tmem::ld8(tbase + T_G + 16 * cA, gA);
-                tmem::ld8(tbase + T_G + 16 * cB, gB);
-                tmem::ld8(tbase + T_D + 16 * cA, dA);
-                tmem::ld8(tbase + T_D + 16 * cB, dB);
+                tmem::ld16(tbase + T_G + 16 * cA, gA, gB);
+                tmem::ld16(tbase + T_D + 16 * cA, dA, dB);
                 if constexpr (!EURO) {
-                    tmem::ld8(tbase + T_P + 16 * cA, pA);
-                    tmem::ld8(tbase + T_P + 16 * cB, pB);
+                    tmem::ld16(tbase + T_P + 16 * cA, pA, pB);
                     tmem::hot_wait(gA, gB, dA);
                     tmem::hot_wait(dB, pA, pB);
                 } else {
@@ -537,10 +533,8 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
                     }
                 }
                 double aA[8], aB[8];
-                tmem::ld8(tbase2 + T_A + 16 * cA, aA);
-                tmem::ld8(tbase2 + T_A + 16 * cB, aB);
-                tmem::ld8(tbase2 + T_G + 16 * cA, gA);
-                tmem::ld8(tbase2 + T_G + 16 * cB, gB);
+                tmem::ld16(tbase2 + T_A + 16 * cA, aA, aB);
+                tmem::ld16(tbase2 + T_G + 16 * cA, gA, gB);
                 tmem::hot_wait(aA, aB);
                 tmem::hot_wait(gA, gB);
                 if constexpr (!D4) {

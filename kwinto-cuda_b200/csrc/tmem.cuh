@@ -51,6 +51,25 @@ __device__ __forceinline__ void ld8(uint32_t taddr, double (&d)[8])
 #pragma unroll
     for (int i = 0; i < 8; ++i) d[i] = __hiloint2double((int)r[2 * i + 1], (int)r[2 * i]);
 }
+// 16 doubles = 32 columns in one instruction (two adjacent 8-double blocks, e.g. the same array of a chunk pair)
+__device__ __forceinline__ void ld16(uint32_t taddr, double (&a)[8], double (&b)[8])
+{
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        a[i] = __hiloint2double((int)r[2 * i + 1], (int)r[2 * i]);
+        b[i] = __hiloint2double((int)r[16 + 2 * i + 1], (int)r[16 + 2 * i]);
+    }
+}
 // the same 8 doubles fetched as two x8 (4 doubles) or four x4 (2 doubles) instructions: smaller
 // destination register blocks are easier to allocate next to long-lived values
 __device__ __forceinline__ void ld8_by4(uint32_t taddr, double (&d)[8])

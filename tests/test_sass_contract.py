@@ -41,12 +41,13 @@ def test_every_ldtm_is_scoreboarded_and_waited_for(contract):
         for n_ldtm, n_sttm, march in hits:
             assert n_ldtm >= 16 and n_sttm >= 4, (key, n_ldtm, n_sttm)
             assert len(march) >= min_loops, (key, len(march))
-    # the headline kernel: every march loop has 24 LDTM per step (a~, g~, D, p + a~, g~ again) and at most 16 moves
+    # the headline kernel: every march loop has 12 LDTM.x32 per step (a~, g~, D, p of a chunk pair + a~, g~ again, two
+    # pairs) and at most 16 moves
     (n_ldtm, n_sttm, march), = [v for k, v in by_name.items() if "fd1d_iw_kernelILi4ELi2ELb0ELb0E" in k]
-    steps = [m for a, b, m in march if m["LDTM"] == 24 and m["DSETP"] == 32]  # the five level-specialised march steps
+    steps = [m for a, b, m in march if m["LDTM"] == 12 and m["DSETP"] == 32]  # the five level-specialised march steps
     assert len(steps) == 5
     for mix in steps:
-        assert mix["LDTM"] == 24 and mix["DFMA"] >= 170 and mix["IMAD"] + mix["MOV"] <= 16, dict(mix)
+        assert mix["LDTM"] == 12 and mix["DFMA"] >= 170 and mix["IMAD"] + mix["MOV"] <= 16, dict(mix)
         assert mix["LDL"] == 0 and mix["STL"] == 0 and mix["LDS"] == 0
 
 
@@ -75,4 +76,4 @@ def test_committed_hot_loop_listing():
     """profiles/ keeps the SASS of the headline march loop with its LDTM / DFMA lines and control words."""
     path = os.path.join(ROOT, "profiles", "r2_sass_hotloop_v237_level2.txt")
     text = open(path).read()
-    assert text.count("LDTM.x16") == 24 and text.count("DFMA") >= 170 and "wait 000001" in text
+    assert text.count("LDTM.x32") == 12 and text.count("DFMA") >= 170 and "wait 000001" in text
