@@ -187,6 +187,13 @@ const RegVariant g_bs2_variant = {257, KW_FD1D_F64, 8, 128, 2, false, false, fd1
                                   IwSmem<4>::bytes(), 256, 4};  // 512 < x <= 1024: the independent-warp kernel, BS = true
 const RegVariant g_bs2n2_variant = {153, KW_FD1D_F64, 8, 64, 2, false, false, fd1d_warp_kernel<2, 2, false, true, 2, true>,
                                     WarpSmem<2>::bytes(), 128, 4};  // 256 < x <= 512, two chunks per lane
+// 1024 < x <= 2048 / 4096: the wide kernels with BS = true
+const RegVariant g_bs_wide2_variant = {356, KW_FD1D_F64, 8, 256, 2, false, false, nullptr, WideSmem<2>::bytes(), 256, 2, 2,
+                                       fd1d_wide_setup_kernel<256>, fd1d_wide_kernel<2, 2, false, true, true>,
+                                       sizeof(double) * 16 * 256, WideSlot<256>::doubles, false};
+const RegVariant g_bs_wide4_variant = {456, KW_FD1D_F64, 8, 512, 2, false, false, nullptr, WideSmem<4>::bytes(), 256, 1, 4,
+                                       fd1d_wide_setup_kernel<512>, fd1d_wide_kernel<4, 2, false, true, true>,
+                                       sizeof(double) * 16 * 512, WideSlot<512>::doubles, false};
 #ifdef KW_EXPERIMENTS
 const RegVariant g_bs253_variant = {253, KW_FD1D_F64, 8, 128, 2, false, false, fd1d_warp_kernel<4, 2, false, true, 2, true>,
                                     WarpSmem<4>::bytes(), 256, 4};  // round 1's fused kernel (CTA-cooperative set-up)
@@ -842,17 +849,20 @@ int kw_fd1d_create(const kw_fd1d_config* cfg, kw_fd1d_handle** out)
         // fused FD1D-BS march: fp64, one Layout W tile of 4 chunks per lane
         const bool tile4 = cfg->x_grid_size > 512 && cfg->x_grid_size <= 1024;
         const bool tile2 = cfg->x_grid_size > 256 && cfg->x_grid_size <= 512;
-        const bool seq = cfg->bs_fused == 0 || cfg->bs_fused == 4;  // variant 253 / 153
-        if (cfg->bs_fused != 1 && cfg->precision == KW_FD1D_F64 && (tile4 || (tile2 && seq)) &&
+        const bool wide2 = cfg->x_grid_size > 1024 && cfg->x_grid_size <= 2048;
+        const bool wide4 = cfg->x_grid_size > 2048 && cfg->x_grid_size <= 4096;
+        const bool seq = cfg->bs_fused == 0 || cfg->bs_fused == 4;  // march as given, then the European copy
+        if (cfg->bs_fused != 1 && cfg->precision == KW_FD1D_F64 && (tile4 || ((tile2 || wide2 || wide4) && seq)) &&
             (cfg->variant == 0 || cfg->bs_fused >= 2)) {
 #ifdef KW_EXPERIMENTS
             h->var_bs = cfg->bs_fused == 2 ? &g_bs1_variant
-                                           : (cfg->bs_fused == 3 ? &g_bs_variant : (tile4 ? &g_bs2_variant : &g_bs2n2_variant));
+                                           : (cfg->bs_fused == 3 ? &g_bs_variant
+                                              : (tile4 ? &g_bs2_variant : (tile2 ? &g_bs2n2_variant : (wide2 ? &g_bs_wide2_variant : &g_bs_wide4_variant))));
 #else
             if (cfg->bs_fused == 2 || cfg->bs_fused == 3)
                 return fail(h, KW_FD1D_EINVAL,
                             "Fd1dGpu_Pricer::init: FD1D.GPU.BS_FUSED = 2 / 3 are experiments (build with -DKW_EXPERIMENTS)");
-            h->var_bs = tile4 ? &g_bs2_variant : &g_bs2n2_variant;
+            h->var_bs = tile4 ? &g_bs2_variant : (tile2 ? &g_bs2n2_variant : (wide2 ? &g_bs_wide2_variant : &g_bs_wide4_variant));
 #endif
             h->bs_forced = cfg->bs_fused >= 2;
             if (int rc = prepare_variant(h, h->var_bs, prop, h->ctas_per_sm_bs, h->regs_bs)) return rc;
@@ -982,10 +992,10 @@ int kw_fd1d_price_bs(kw_fd1d_handle* h, const kw_option* assets, size_t n, doubl
     KW_CUDA(h, h->d_prices.reserve(n));
     KW_CUDA(h, h->d_prices2.reserve(n));
     if (h->cfg.bs_fused >= 2 && !h->var_bs)
-        return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::price: FD1D.GPU.BS_FUSED = 2 / 3 needs fp64 and 512 < FD1D.X_GRID_SIZE <= 1024, = 4 fp64 and 256 < FD1D.X_GRID_SIZE <= 1024");
+        return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::price: FD1D.GPU.BS_FUSED = 2 / 3 needs fp64 and 512 < FD1D.X_GRID_SIZE <= 1024, = 4 fp64 and 256 < FD1D.X_GRID_SIZE <= 4096");
     // auto: fused from one full wave of the persistent grid (4 chains per CTA) upwards; below that the
     // CTA-per-PDE kernel of the two-solve path spreads the batch over more SMs
-    if (h->var_bs && (h->bs_forced || n >= (size_t)h->sm_count * h->ctas_per_sm_bs * 3)) {  // 3/4 of a wave, as small_below
+    if (h->var_bs && (h->bs_forced || 4 * n >= (size_t)h->sm_count * h->ctas_per_sm_bs * h->var_bs->pdes_per_cta * 3)) {  // 3/4 of a wave, as small_below
         // fused: the solve as given (:18) and the solve of the European copies (:21-28) are two value
         // vectors of the same chains marched by one launch; then + (BS - FD_euro) (:30-40)
         if (int rc = price_to_device(h, assets, n, h->d_opts, h->d_prices.p, h->d_prices2.p)) return rc;
@@ -1288,7 +1298,7 @@ int kw_fd1d_has_variant(int32_t id, int32_t precision)
 {
     for (int i = 0; i < kNumVariants; ++i)
         if (g_variants[i].id == id && g_variants[i].prec == precision) return 1;
-    if (precision == KW_FD1D_F64 && (id == g_bs2_variant.id || id == g_bs2n2_variant.id)) return 1;
+    if (precision == KW_FD1D_F64 && (id == g_bs2_variant.id || id == g_bs2n2_variant.id || id == g_bs_wide2_variant.id || id == g_bs_wide4_variant.id)) return 1;
 #ifdef KW_EXPERIMENTS
     if (precision == KW_FD1D_F64 && (id == g_bs_variant.id || id == g_bs1_variant.id || id == g_bs253_variant.id)) return 1;
 #endif

@@ -115,11 +115,15 @@ __device__ __forceinline__ void group_barrier(int grp)
 }
 
 // SPLIT: as in fd1d_warp.cuh -- every chunk-pair phase a basic block of its own, a~ and g~ loaded twice.
-template <int NWP, int MINB, bool ICMP, bool SPLIT = false>
+// BS (with SPLIT): the fused FD1D-BS march -- the PDE's warps march the chain as given, price it into B.prices, re-create the
+// payoff and march the European copy (no floor, no compare) with a~, g~, D still in tensor memory into B.prices_eu; a chain given
+// as European is marched once and priced into both arrays (reference src/Pricer/kwFd1d_BlackScholes.cpp:15-43).
+template <int NWP, int MINB, bool ICMP, bool SPLIT = false, bool BS = false>
 __global__ void __launch_bounds__(128, MINB) fd1d_wide_kernel(const Fd1dBatch B, const double* __restrict__ ws,
                                                                uint32_t pde_base, uint32_t count)
 {
     static_assert(NWP == 2 || NWP == 4, "two or four warps per PDE");
+    static_assert(!BS || SPLIT, "the fused FD1D-BS march exists in the rotated split form only");
     constexpr int NCH = 4;
     constexpr int NODES = 32;                 // per lane
     constexpr int PPC = 4 / NWP;
@@ -429,8 +433,9 @@ __global__ void __launch_bounds__(128, MINB) fd1d_wide_kernel(const Fd1dBatch B,
             // block, a~ / g~ loaded twice, and the NEXT step's scans (with their two named barriers) issued behind the
             // last pair's local sweeps with pair 0's forward sweeps behind them, so that shuffle, shared-memory and
             // barrier latency hides behind sweeps of the same basic block.
-            auto march_rot = [&](auto lev_c) {
+            auto march_rot = [&](auto lev_c, auto euro_c) {
                 constexpr int LEV = decltype(lev_c)::value;
+                constexpr bool EURO = decltype(euro_c)::value;  // European copy: no floor, no compare
                 double kA[NCH], kG[NCH], kR[NCH], kAf[LEV], kGb[LEV];
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) {
@@ -529,10 +534,15 @@ __global__ void __launch_bounds__(128, MINB) fd1d_wide_kernel(const Fd1dBatch B,
                     tmem::ld8(tbase + T_G + 16 * cB, gB);
                     tmem::ld8(tbase + T_D + 16 * cA, dA);
                     tmem::ld8(tbase + T_D + 16 * cB, dB);
-                    tmem::ld8(tbase + T_P + 16 * cA, pA);
-                    tmem::ld8(tbase + T_P + 16 * cB, pB);
-                    tmem::hot_wait(gA, gB, dA);
-                    tmem::hot_wait(dB, pA, pB);
+                    if constexpr (!EURO) {
+                        tmem::ld8(tbase + T_P + 16 * cA, pA);
+                        tmem::ld8(tbase + T_P + 16 * cB, pB);
+                        tmem::hot_wait(gA, gB, dA);
+                        tmem::hot_wait(dB, pA, pB);
+                    } else {
+                        tmem::hot_wait(gA, gB);
+                        tmem::hot_wait(dA, dB);
+                    }
                     double uA = Uin[cA], uB = Uin[cB];
 #pragma unroll
                     for (int i = 7; i >= 0; --i) {
@@ -540,8 +550,13 @@ __global__ void __launch_bounds__(128, MINB) fd1d_wide_kernel(const Fd1dBatch B,
                         uB = fma(gB[i], uB, yB[i]);
                         const double rA = fma(dA[i], uA, -vr[8 * cA + i]);
                         const double rB = fma(dB[i], uB, -vr[8 * cB + i]);
-                        vr[8 * cA + i] = ICMP ? max_like_icmp(rA, pA[i]) : max_like_std(rA, pA[i]);
-                        vr[8 * cB + i] = ICMP ? max_like_icmp(rB, pB[i]) : max_like_std(rB, pB[i]);
+                        if constexpr (EURO) {
+                            vr[8 * cA + i] = rA;
+                            vr[8 * cB + i] = rB;
+                        } else {
+                            vr[8 * cA + i] = ICMP ? max_like_icmp(rA, pA[i]) : max_like_std(rA, pA[i]);
+                            vr[8 * cB + i] = ICMP ? max_like_icmp(rB, pB[i]) : max_like_std(rB, pB[i]);
+                        }
                     }
                     double aA[8], aB[8];
                     tmem::ld8(tbase2 + T_A + 16 * cA, aA);
@@ -595,39 +610,66 @@ __global__ void __launch_bounds__(128, MINB) fd1d_wide_kernel(const Fd1dBatch B,
             };
             // the PDE's warps share barriers, so they must agree on nothing but the step count; each picks
             // its own number of in-warp levels
-            if constexpr (SPLIT) {
-                switch (levels) {
-                    case 1: march_rot(std::integral_constant<int, 1>{}); break;
-                    case 2: march_rot(std::integral_constant<int, 2>{}); break;
-                    case 3: march_rot(std::integral_constant<int, 3>{}); break;
-                    case 4: march_rot(std::integral_constant<int, 4>{}); break;
-                    default: march_rot(std::integral_constant<int, 5>{}); break;
+            auto march_levels = [&](auto euro_c) {
+                if constexpr (SPLIT) {
+                    switch (levels) {
+                        case 1: march_rot(std::integral_constant<int, 1>{}, euro_c); break;
+                        case 2: march_rot(std::integral_constant<int, 2>{}, euro_c); break;
+                        case 3: march_rot(std::integral_constant<int, 3>{}, euro_c); break;
+                        case 4: march_rot(std::integral_constant<int, 4>{}, euro_c); break;
+                        default: march_rot(std::integral_constant<int, 5>{}, euro_c); break;
+                    }
+                } else {
+                    switch (levels) {
+                        case 1: march(std::integral_constant<int, 1>{}); break;
+                        case 2: march(std::integral_constant<int, 2>{}); break;
+                        case 3: march(std::integral_constant<int, 3>{}); break;
+                        case 4: march(std::integral_constant<int, 4>{}); break;
+                        default: march(std::integral_constant<int, 5>{}); break;
+                    }
                 }
-            } else
-            switch (levels) {
-                case 1: march(std::integral_constant<int, 1>{}); break;
-                case 2: march(std::integral_constant<int, 2>{}); break;
-                case 3: march(std::integral_constant<int, 3>{}); break;
-                case 4: march(std::integral_constant<int, 4>{}); break;
-                default: march(std::integral_constant<int, 5>{}); break;
-            }
-            if (lane == 0 && wq == 0) {
-                const int bucket = B.max_mode == 0 ? 0 : (levels == 5 ? 1 : 6 - levels);
-                atomicAdd(&B.status[2 + bucket], 1u);
-            }
-            // ---------------- epilogue -------------------------------------------------------------
+            };
+            const uint32_t rep_e = B.pde_rep ? __ldg(B.pde_rep + my_pde) : my_pde;
+            const PdeScalars sc_e = pde_scalars(load_option(B.opts + rep_e), B);
+            // ---------------- epilogue: every option of the chain, interpolated by the PDE's warps ------------------
+            auto emit = [&](double* out) {
 #pragma unroll
-            for (int i = 0; i < NODES; ++i) vfin[(wq * 32 + lane) * NODES + i] = vr[i];
-            group_barrier<32 * NWP>(grp);
-            {
-                const uint32_t rep = B.pde_rep ? __ldg(B.pde_rep + my_pde) : my_pde;
-                const PdeScalars sc = pde_scalars(load_option(B.opts + rep), B);
+                for (int i = 0; i < NODES; ++i) vfin[(wq * 32 + lane) * NODES + i] = vr[i];
+                group_barrier<32 * NWP>(grp);
+                Fd1dBatch Bo = B;
+                Bo.prices = out;
                 uint32_t q0, q1;
                 chain_range(B, my_pde, q0, q1);
                 for (uint32_t q = q0 + wq * 32 + lane; q < q1; q += 32 * NWP) {
                     const uint32_t oi = B.csr_opt ? __ldg(B.csr_opt + q) : q;
-                    price_option(B, oi, [&](int j) { return x_node(sc, B.density, j); }, [&](int j) { return vfin[j]; });
+                    price_option(Bo, oi, [&](int j) { return x_node(sc_e, B.density, j); }, [&](int j) { return vfin[j]; });
                 }
+                group_barrier<32 * NWP>(grp);  // vfin is rewritten by the next emit
+            };
+            march_levels(std::false_type{});
+            if (lane == 0 && wq == 0) {
+                const int bucket = B.max_mode == 0 ? 0 : (levels == 5 ? 1 : 6 - levels);
+                atomicAdd(&B.status[2 + bucket], 1u);
+            }
+            emit(B.prices);
+            if constexpr (BS) {
+                if (sc_e.american) {  // uniform over the PDE's warps
+                    // the European copy: payoff again (src/Pricer/kwFd1d.cpp:127-139, as the set-up kernel computed it)
+#pragma unroll 1
+                    for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int j = (wq * 32 + lane) * NODES + 8 * c + i;
+                            vfin[j] = j < xDim ? payoff_node(sc_e.put, x_node(sc_e, B.density, j)) : 0.;
+                        }
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < NODES; ++i) vr[i] = vfin[(wq * 32 + lane) * NODES + i];
+                    __syncwarp();
+                    march_levels(std::true_type{});
+                }
+                emit(B.prices_eu);  // a chain given as European: one march, both arrays
             }
         }
         __syncthreads();  // vfin, the exchange slots and the TMEM arrays are rewritten by the next PDE

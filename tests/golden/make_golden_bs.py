@@ -43,6 +43,10 @@ def main():
         # the two-chunk tile (256 < x <= 512), incl. the reference's default grid 512 x 512
         ("bs_512", with_chain_members(synthetic_options(1300, 24, european_every=6, call_every=4), 5, 3), 512, 512),
         ("bs_300x100", with_chain_members(synthetic_options(90, 25, european_every=3, call_every=2), 3, 4), 100, 300),
+        # the wide tiles (round 2: fused march on the two- and four-warp kernels)
+        ("bs_2048", with_chain_members(synthetic_options(200, 26, european_every=5, call_every=3), 4, 5), 2048, 2048),
+        ("bs_4096x256", with_chain_members(synthetic_options(120, 27, european_every=4, call_every=3), 4, 6), 256, 4096),
+        ("bs_1500x96", with_chain_members(synthetic_options(60, 28, european_every=3, call_every=2), 3, 7), 96, 1500),
     ]
     for key, o, t, x in cases:
         out[key + "/options"] = o

@@ -88,7 +88,8 @@ def test_synthetic_golden_all_shapes():
 
 @pytest.mark.parametrize("key,fused,variant", [(k, f, v) for k in ("bs_1024", "bs_700x200", "bs_513x64")
                                                for f, v in ((4, 257), (3, 252), (2, 251))] +
-                         [(k, 4, 153) for k in ("bs_512", "bs_300x100")])
+                         [(k, 4, 153) for k in ("bs_512", "bs_300x100")] +
+                         [("bs_2048", 4, 356), ("bs_1500x96", 4, 356), ("bs_4096x256", 4, 456)])
 def test_fd1d_bs_fused_march(key, fused, variant):
     # src/Pricer/kwFd1d_BlackScholes.cpp:15-43 with both solves of a chain marched by one launch --
     # variant 253 (153 for 256 < x <= 512): every warp marches its chain as given, then the European copy
