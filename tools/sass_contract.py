@@ -31,8 +31,10 @@ DEFAULT_LIB = os.path.join(ROOT, "kwinto-cuda_b200", "lib", "libkwfd1d.so")
 MARCH_KERNELS = ("fd1d_iw_kernel", "fd1d_warp_kernel", "fd1d_wide_kernel", "fd1d_warpf_kernel", "fd1d_warp2_kernel",
                  "fd1d_warp_bs_kernel", "fd1d_reg_kernel")
 # rule 3 (no spills inside the march loop) is a hard rule for the kernels the dispatch picks for full devices;
-# elsewhere it is reported as a warning (experiments build: the round-1 wide kernels 331 / 431 keep 1-2 LDL per step)
-NO_SPILL_KERNELS = ("fd1d_iw_kernel", "fd1d_wide_kernelILi4ELi2ELb0ELb1", "fd1d_wide_kernelILi2ELi2ELb0ELb1", "fd1d_warpf_kernel")
+# elsewhere it is reported as a warning (the fused FD1D-BS wide kernel re-reads up to 3 loop invariants in one of its ten
+# loops; experiments build: the round-1 wide kernels 331 / 431 keep 1-2 LDL per step)
+NO_SPILL_KERNELS = ("fd1d_iw_kernel", "fd1d_wide_kernelILi4ELi2ELb0ELb1ELb0", "fd1d_wide_kernelILi2ELi2ELb0ELb1ELb0",
+                    "fd1d_warpf_kernel")
 WIDE_OPS = ("DFMA", "DADD", "DMUL", "DSETP", "DMNMX", "F2F.F64", "I2F.F64", "MUFU.RCP64H", "MUFU.RSQ64H")
 
 
