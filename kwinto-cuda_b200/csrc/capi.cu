@@ -87,6 +87,11 @@ struct RegVariant {
         ID, KW_FD1D_F64, 8, 32 * NCH_, MINB_, false, false, fd1d_iw_kernel<NCH_, MINB_>,           \
             IwSmem<NCH_>::bytes(), 64 * NCH_, 4                                                    \
     }
+#define KW_VARIANT_IWP(ID, PACK_)                                                                 \
+    {                                                                                              \
+        ID, KW_FD1D_F64, 8, 128 / PACK_, 2, false, false, fd1d_iw_kernel<4, 2, false, false, PACK_>, \
+            IwSmem<4>::bytes(), 256, 4 * PACK_                                                     \
+    }
 #define KW_VARIANT_WRT(ID, MINB_)                                                                 \
     {                                                                                              \
         ID, KW_FD1D_F64, 8, 128, MINB_, false, false, fd1d_warp_kernel<4, MINB_, false, true, 0, true>, \
@@ -129,9 +134,10 @@ struct RegVariant {
 // kernels the dispatch can reach; every other variant measured along the way (DESIGN.md "Tried") is compiled only
 // with -DKW_EXPERIMENTS (make EXPERIMENTS=1), so that they cost no build time, binary size or test matrix by default.
 const RegVariant g_variants[] = {
-    KW_VARIANT(1, 8, 32, 12, false, false),    // x <= 256
-    KW_VARIANT_WN(133, 2, 2),                  // x <= 512: Layout W with 2 chunks per lane (one chunk pair)
-    KW_VARIANT(101, 8, 64, 6, false, false),   // x <= 512, CTA per PDE (batches below one wave of Layout W)
+    KW_VARIANT_IWP(38, 4),                     // x <= 256: 237 with four PDEs per warp (8 lanes each; 1.87 vs 2.31 ms at 256^2)
+    KW_VARIANT(1, 8, 32, 12, false, false),    // x <= 256, CTA per PDE (small batches)
+    KW_VARIANT_IWP(138, 2),                    // x <= 512: 237 with two PDEs per warp (16 lanes each; 6.36 vs 7.03 ms at 512^2)
+    KW_VARIANT(101, 8, 64, 6, false, false),   // x <= 512, CTA per PDE (small batches)
     KW_VARIANT_IW(237, 4, 2),                  // x <= 1024: Layout W with independent warps (fd1d_iw.cuh): warp-level set-up, no CTA
                                                // barrier, PDEs handed out by an atomic counter, rotated split march (23.9 ms)
     KW_VARIANT(201, 8, 128, 3, false, false),  // x <= 1024, CTA per PDE (batches below one wave of Layout W)
@@ -166,6 +172,7 @@ const RegVariant g_variants[] = {
     KW_VARIANT_W(232, 2, true, false),
     KW_VARIANT_W(231, 2, false, false),  // one chunk at a time, next chunk's a~ prefetched
     KW_VARIANT_W(234, 2, true, true),
+    KW_VARIANT_WN(133, 2, 2),  // the round-1 default for x <= 512: Layout W with 2 chunks per lane (one chunk pair)
     KW_VARIANT_IW(137, 2, 2),  // 237's two-chunk twin (7.30 ms at 512^2 against 6.91 for 133)
     KW_VARIANT_WS(136, 2, 2),  // 133 in the form of 236 (slower on the two-chunk tile: 7.65 vs 6.92 ms at 512^2)
     KW_VARIANT_WRT(235, 2),  // 233 with the scan-level count as a run-time value: one march loop instead of five
@@ -179,14 +186,16 @@ const RegVariant g_variants[] = {
 #endif
 };
 // fused FD1D-BS marches (one set-up and one tensor-memory copy of a~, g~, D for the solve as given and the
-// solve of the European copy).  257 (fd1d_iw.cuh, BS) / 153 (fd1d_warp.cuh, BS = 2), default where they apply: every
+// solve of the European copy).  257 / 158 / 58 (fd1d_iw.cuh, BS; one, two, four PDEs per warp), default where they apply: every
 // warp marches its chain as given, then the European copy.  Experiments: 252 (FD1D.GPU.BS_FUSED = 3; BS = 1): eight warps per CTA,
 // warp w marches PDE w as given while warp w + 4 marches the European copy; 251 (FD1D.GPU.BS_FUSED = 2;
 // fd1d_warp_bs.cuh): both solutions in one warp's step (instruction-cache bound, slower than two solves).
 const RegVariant g_bs2_variant = {257, KW_FD1D_F64, 8, 128, 2, false, false, fd1d_iw_kernel<4, 2, true>,
                                   IwSmem<4>::bytes(), 256, 4};  // 512 < x <= 1024: the independent-warp kernel, BS = true
-const RegVariant g_bs2n2_variant = {153, KW_FD1D_F64, 8, 64, 2, false, false, fd1d_warp_kernel<2, 2, false, true, 2, true>,
-                                    WarpSmem<2>::bytes(), 128, 4};  // 256 < x <= 512, two chunks per lane
+const RegVariant g_bs2n2_variant = {158, KW_FD1D_F64, 8, 64, 2, false, false, fd1d_iw_kernel<4, 2, true, false, 2>,
+                                    IwSmem<4>::bytes(), 256, 8};  // 256 < x <= 512: two PDEs per warp
+const RegVariant g_bs2n1_variant = {58, KW_FD1D_F64, 8, 32, 2, false, false, fd1d_iw_kernel<4, 2, true, false, 4>,
+                                    IwSmem<4>::bytes(), 256, 16};  // x <= 256: four PDEs per warp
 // 1024 < x <= 2048 / 4096: the wide kernels with BS = true
 const RegVariant g_bs_wide2_variant = {356, KW_FD1D_F64, 8, 256, 2, false, false, nullptr, WideSmem<2>::bytes(), 256, 2, 2,
                                        fd1d_wide_setup_kernel<256>, fd1d_wide_kernel<2, 2, false, true, true>,
@@ -844,25 +853,29 @@ int kw_fd1d_create(const kw_fd1d_config* cfg, kw_fd1d_handle** out)
                 // 0.27 ms at 512^2), the CTA-per-PDE kernel needs a second and third round from 444 / 888 PDEs on:
                 // measured crossover at ~0.7 of a wave (profiles/r1_bv_small_batch_crossover.log)
                 if (h->var->pdes_per_cta == 4 && !h->var->wide_nwp) h->small_below = h->small_below * 3 / 4;
+                // packed warps (two / four PDEs per warp): a batch of up to half a wave takes one lone-warp period whatever its
+                // size; the CTA-per-PDE kernel wins only while it needs a single round of its own
+                if (h->var->pdes_per_cta > 4) h->small_below = (uint32_t)(h->sm_count * h->ctas_per_sm_small) + 1;
             }
         }
         // fused FD1D-BS march: fp64, one Layout W tile of 4 chunks per lane
         const bool tile4 = cfg->x_grid_size > 512 && cfg->x_grid_size <= 1024;
         const bool tile2 = cfg->x_grid_size > 256 && cfg->x_grid_size <= 512;
+        const bool tile1 = cfg->x_grid_size <= 256;
         const bool wide2 = cfg->x_grid_size > 1024 && cfg->x_grid_size <= 2048;
         const bool wide4 = cfg->x_grid_size > 2048 && cfg->x_grid_size <= 4096;
         const bool seq = cfg->bs_fused == 0 || cfg->bs_fused == 4;  // march as given, then the European copy
-        if (cfg->bs_fused != 1 && cfg->precision == KW_FD1D_F64 && (tile4 || ((tile2 || wide2 || wide4) && seq)) &&
+        if (cfg->bs_fused != 1 && cfg->precision == KW_FD1D_F64 && (tile4 || ((tile1 || tile2 || wide2 || wide4) && seq)) &&
             (cfg->variant == 0 || cfg->bs_fused >= 2)) {
 #ifdef KW_EXPERIMENTS
             h->var_bs = cfg->bs_fused == 2 ? &g_bs1_variant
                                            : (cfg->bs_fused == 3 ? &g_bs_variant
-                                              : (tile4 ? &g_bs2_variant : (tile2 ? &g_bs2n2_variant : (wide2 ? &g_bs_wide2_variant : &g_bs_wide4_variant))));
+                                              : (tile4 ? &g_bs2_variant : (tile2 ? &g_bs2n2_variant : (tile1 ? &g_bs2n1_variant : (wide2 ? &g_bs_wide2_variant : &g_bs_wide4_variant)))));
 #else
             if (cfg->bs_fused == 2 || cfg->bs_fused == 3)
                 return fail(h, KW_FD1D_EINVAL,
                             "Fd1dGpu_Pricer::init: FD1D.GPU.BS_FUSED = 2 / 3 are experiments (build with -DKW_EXPERIMENTS)");
-            h->var_bs = tile4 ? &g_bs2_variant : (tile2 ? &g_bs2n2_variant : (wide2 ? &g_bs_wide2_variant : &g_bs_wide4_variant));
+            h->var_bs = tile4 ? &g_bs2_variant : (tile2 ? &g_bs2n2_variant : (tile1 ? &g_bs2n1_variant : (wide2 ? &g_bs_wide2_variant : &g_bs_wide4_variant)));
 #endif
             h->bs_forced = cfg->bs_fused >= 2;
             if (int rc = prepare_variant(h, h->var_bs, prop, h->ctas_per_sm_bs, h->regs_bs)) return rc;
@@ -992,10 +1005,10 @@ int kw_fd1d_price_bs(kw_fd1d_handle* h, const kw_option* assets, size_t n, doubl
     KW_CUDA(h, h->d_prices.reserve(n));
     KW_CUDA(h, h->d_prices2.reserve(n));
     if (h->cfg.bs_fused >= 2 && !h->var_bs)
-        return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::price: FD1D.GPU.BS_FUSED = 2 / 3 needs fp64 and 512 < FD1D.X_GRID_SIZE <= 1024, = 4 fp64 and 256 < FD1D.X_GRID_SIZE <= 4096");
+        return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::price: FD1D.GPU.BS_FUSED = 2 / 3 needs fp64 and 512 < FD1D.X_GRID_SIZE <= 1024, = 4 fp64 and FD1D.X_GRID_SIZE <= 4096");
     // auto: fused from one full wave of the persistent grid (4 chains per CTA) upwards; below that the
     // CTA-per-PDE kernel of the two-solve path spreads the batch over more SMs
-    if (h->var_bs && (h->bs_forced || 4 * n >= (size_t)h->sm_count * h->ctas_per_sm_bs * h->var_bs->pdes_per_cta * 3)) {  // 3/4 of a wave, as small_below
+    if (h->var_bs && (h->bs_forced || 4 * n >= (size_t)h->sm_count * h->ctas_per_sm_bs * std::min(4, h->var_bs->pdes_per_cta) * 3)) {  // 3/4 of a wave, as small_below
         // fused: the solve as given (:18) and the solve of the European copies (:21-28) are two value
         // vectors of the same chains marched by one launch; then + (BS - FD_euro) (:30-40)
         if (int rc = price_to_device(h, assets, n, h->d_opts, h->d_prices.p, h->d_prices2.p)) return rc;
@@ -1126,7 +1139,7 @@ int kw_fd1d_get_info(const kw_fd1d_handle* hc, kw_fd1d_info* info)
     const bool lsmall = lv && lv == h->var_small;
     info->variant = lv ? lv->id : 0;
     const bool lw = lv && (lv->pdes_per_cta > 1 || lv->wide_nwp);  // Layout W: 32 nodes per lane
-    info->threads_per_pde = lv ? (lv->wide_nwp ? 32 * lv->wide_nwp : (lw ? 32 : lv->P)) : 1;
+    info->threads_per_pde = lv ? (lv->wide_nwp ? 32 * lv->wide_nwp : (lw ? 128 / lv->pdes_per_cta : lv->P)) : 1;
     info->nodes_per_thread = lv ? (lw ? 32 : lv->M) : (int)h->cfg.x_grid_size;
     const bool lbs = lv && lv == h->var_bs;
     info->ctas_per_sm = lbs ? h->ctas_per_sm_bs : (lsmall ? h->ctas_per_sm_small : h->ctas_per_sm);
@@ -1298,7 +1311,7 @@ int kw_fd1d_has_variant(int32_t id, int32_t precision)
 {
     for (int i = 0; i < kNumVariants; ++i)
         if (g_variants[i].id == id && g_variants[i].prec == precision) return 1;
-    if (precision == KW_FD1D_F64 && (id == g_bs2_variant.id || id == g_bs2n2_variant.id || id == g_bs_wide2_variant.id || id == g_bs_wide4_variant.id)) return 1;
+    if (precision == KW_FD1D_F64 && (id == g_bs2_variant.id || id == g_bs2n2_variant.id || id == g_bs2n1_variant.id || id == g_bs_wide2_variant.id || id == g_bs_wide4_variant.id)) return 1;
 #ifdef KW_EXPERIMENTS
     if (precision == KW_FD1D_F64 && (id == g_bs_variant.id || id == g_bs1_variant.id || id == g_bs253_variant.id)) return 1;
 #endif

@@ -53,16 +53,29 @@ struct IwSmem {
 // dependent depth of 20 instead of 30 DFMAs per pair: the march is bound by the 8-cycle dependent-issue latency of the chains
 // two warps can keep in flight, not by the FP64 pipe.  Five constants per chunk and the two carried
 // half-chunk values live in the warp's shared scratch ([row][lane], one LDS / STS per use).
-template <int NCH, int MINB, bool BS = false, bool D4 = false>
+// PACK: PDEs per warp (1, 2 or 4).  A grid of at most 8*NCH*32 / PACK nodes takes only 32 / PACK lanes, so PACK PDEs ride
+// in one warp side by side: lanes [h * LPP, (h + 1) * LPP) own PDE h of the warp's work unit.  The march needs no change at
+// all: the first row of every PDE has no sub-diagonal (a~ = 0) and its last row no super-diagonal (g~ = 0), so the products the
+// lane scans carry across a PDE boundary are exactly zero, and the shuffles are confined to a PDE's lanes by their width argument
+// (nothing, not even a NaN, crosses over).  The step then costs what a full-tile PDE's step costs and advances PACK PDEs: the
+// 512-node grid runs at the instruction mix of the 1024-node kernel (4 chunks per lane, two chunk pairs, rotated loop) instead of
+// the single-pair loop of NCH = 2, whose scans have no sweeps to hide behind.
+template <int NCH, int MINB, bool BS = false, bool D4 = false, int PACK = 1>
 __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
 {
     static_assert(NCH == 4 || NCH == 2, "4 chunks per lane (512 < x <= 1024) or 2 (256 < x <= 512)");
+    static_assert(PACK == 1 || PACK == 2 || PACK == 4, "1, 2 or 4 PDEs per warp");
     constexpr int N = IwSmem<NCH>::N;
     constexpr int NODES = 8 * NCH;  // per lane
+    constexpr int LPP = 32 / PACK;  // lanes per PDE
+    constexpr int XT = N / PACK;    // nodes per PDE tile
+    constexpr int MAXLEV = PACK == 1 ? 5 : (PACK == 2 ? 4 : 3);  // Kogge-Stone levels that stay inside a PDE
 
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+    const int pl = lane & (LPP - 1);  // lane within its PDE
+    const int ph = lane / LPP;        // which PDE of the warp's work unit
     double* vfin = smem + warp * (N + IwSmem<NCH>::SCR);
     double* scr = vfin + N;
     const int xDim = B.xDim;
@@ -81,9 +94,12 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
     const uint32_t n_pde = batch_n_pde(B);
     for (;;) {
         uint32_t my_pde = 0;
-        if (lane == 0) my_pde = atomicAdd(B.work_counter, 1u);
-        my_pde = __shfl_sync(FULL, my_pde, 0);
+        if (lane == 0) my_pde = atomicAdd(B.work_counter, 1u);  // work unit = PACK consecutive PDEs
+        my_pde = __shfl_sync(FULL, my_pde, 0) * PACK;
         if (my_pde >= n_pde) break;
+        my_pde += ph;
+        const bool live = my_pde < n_pde;  // a short last unit: the spare lanes shadow the last PDE and emit nothing
+        if (!live) my_pde = n_pde - 1;
 
         const uint32_t rep = B.pde_rep ? __ldg(B.pde_rep + my_pde) : my_pde;
         const kw_option opt = load_option(B.opts + rep);
@@ -98,16 +114,16 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
         // boundary travels in a loop-carried scalar, in tensor memory (the rows of B, then 1/beta in the diagonal's
         // columns) or in the warp's shared scratch ([index][lane], conflict-free).
         {
-            const int j0 = lane * NODES;
+            const int j0 = pl * NODES;
             double* s_v = vfin;            // [NODES][32] payoff, until the registers take it
             double* s_k = scr + 28 * 32;   // [3 * NCH][32] chunk scalars
             double* s_h = scr;             // [5 * NCH][32] half-chunk constants P_lo, P_hi, Q_lo, Q_hi, R_hi (D4)
             // ---- grid, payoff, projection floor, rows of B (parked in tensor memory)
             double bu_carry = 0.;
             {
-                double x_m1 = lane ? x_node_ni(sc, B.density, j0 - 1) : 0.;
+                double x_m1 = pl ? x_node_ni(sc, B.density, j0 - 1) : 0.;
                 double x_0 = x_node_ni(sc, B.density, j0);
-                if (lane == 0) x_m1 = x_0;
+                if (pl == 0) x_m1 = x_0;
 #pragma unroll 1
                 for (int c = 0; c < NCH; ++c) {
                     double xl[10];  // nodes 8c - 1 .. 8c + 8 of this lane
@@ -115,7 +131,7 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
                     xl[1] = x_0;
 #pragma unroll
                     for (int i = 1; i <= 8; ++i) xl[1 + i] = x_node_ni(sc, B.density, j0 + 8 * c + i);
-                    if (lane == 31 && c == NCH - 1) xl[9] = xl[8];  // past the tile: the last node again
+                    if (pl == LPP - 1 && c == NCH - 1) xl[9] = xl[8];  // past the tile: the last node again
                     double t8[8], bl[8], bb[8], bu[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -137,8 +153,8 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
                 }
                 tmem::wait_st();
             }
-            double bu_prev_lane = __shfl_up_sync(FULL, bu_carry, 1);
-            if (lane == 0) bu_prev_lane = 0.;
+            double bu_prev_lane = __shfl_up_sync(FULL, bu_carry, 1, LPP);
+            if (pl == 0) bu_prev_lane = 0.;
             // ---- pivots: beta_j = b_j - c_j / beta_{j-1}, c_j = bl_j bu_{j-1}, as the Moebius map
             //      [[b_j, -c_j], [1, 0]] on (num; den); compose per chunk, per lane, scan over the lanes
             {
@@ -168,16 +184,16 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
                     mat_normalise(Lm);
                 }
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const Mat2 o = mat_shfl_up(Lm, d);
-                    if (lane >= d) {
+                for (int d = 1; d < LPP; d <<= 1) {
+                    const Mat2 o = mat_shfl_up(Lm, d, LPP);
+                    if (pl >= d) {
                         Lm = mat_mul(Lm, o);
                         mat_normalise(Lm);
                     }
                 }
-                const Mat2 E = mat_shfl_up(Lm, 1);
-                double num = lane ? E.m00 : 1.;
-                double den = lane ? E.m10 : 0.;
+                const Mat2 E = mat_shfl_up(Lm, 1, LPP);
+                double num = pl ? E.m00 : 1.;
+                double den = pl ? E.m10 : 0.;
                 // ---- The scan's pivots are a first guess only.  The recurrence beta_j = b_j - c_j / beta_{j-1} contracts
                 //      (d beta_j / d beta_{j-1} = c_j / beta_{j-1}^2 < 1), so run serially it forgets its rounding errors,
                 //      while the composed maps accumulate theirs over the whole grid (1e-13 relative at 4096 nodes: on stiff
@@ -205,8 +221,8 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
                         }
                         bu_carry = bu[7];
                     }
-                    double pnew = __shfl_up_sync(FULL, prev, 1);
-                    if (lane == 0) pnew = CUDART_INF;
+                    double pnew = __shfl_up_sync(FULL, prev, 1, LPP);
+                    if (pl == 0) pnew = CUDART_INF;
                     const bool changed = __double_as_longlong(pnew) != __double_as_longlong(pin);
                     pin = pnew;
                     if (!__any_sync(FULL, changed)) break;
@@ -247,10 +263,10 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
                     tmem::wait_ld_dep(t);
                     ib_last_lane = t[7];
                 }
-                double ib_prev = __shfl_up_sync(FULL, ib_last_lane, 1);    // 1/beta of the node before the chunk
-                double ib_next_lane = __shfl_down_sync(FULL, ib_first_lane, 1);
-                if (lane == 0) ib_prev = 0.;
-                if (lane == 31) ib_next_lane = 0.;
+                double ib_prev = __shfl_up_sync(FULL, ib_last_lane, 1, LPP);    // 1/beta of the node before the chunk
+                double ib_next_lane = __shfl_down_sync(FULL, ib_first_lane, 1, LPP);
+                if (pl == 0) ib_prev = 0.;
+                if (pl == LPP - 1) ib_next_lane = 0.;
 #pragma unroll 1
                 for (int c = 0; c < NCH; ++c) {
                     double bl[8], bu[8], ibn[8];
@@ -305,7 +321,7 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
                 tmem::wait_st();
             }
 #pragma unroll
-            for (int d = 16; d >= 1; d >>= 1) bmax = fmax(bmax, __shfl_xor_sync(FULL, bmax, d));
+            for (int d = LPP / 2; d >= 1; d >>= 1) bmax = fmax(bmax, __shfl_xor_sync(FULL, bmax, d));  // over the PDE's lanes
             __syncwarp();
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
@@ -331,43 +347,56 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
 #pragma unroll
             for (int d = 0; d < 5; ++d) {
                 const int s = 1 << d;
-                const double o = __shfl_up_sync(FULL, A, s);
-                AfL[d] = lane >= s ? A : 0.;
-                if (lane >= s) A *= o;
+                const double o = __shfl_up_sync(FULL, A, s, LPP);
+                AfL[d] = pl >= s ? A : 0.;
+                if (pl >= s) A *= o;
             }
             double G = GL;
 #pragma unroll
             for (int d = 0; d < 5; ++d) {
                 const int s = 1 << d;
-                const double o = __shfl_down_sync(FULL, G, s);
-                GbL[d] = lane < 32 - s ? G : 0.;
-                if (lane < 32 - s) G *= o;
+                const double o = __shfl_down_sync(FULL, G, s, LPP);
+                GbL[d] = pl < LPP - s ? G : 0.;
+                if (pl < LPP - s) G *= o;
             }
         }
-        // keep the multipliers as values: the compiler would otherwise re-derive the first levels from Ac[] / Gc[]
-        // inside the march loop (6 DMUL + the lane predicate per step) to save two registers
-#pragma unroll
-        for (int d = 0; d < 5; ++d) asm volatile("" : "+d"(AfL[d]), "+d"(GbL[d]));
         auto kA = [&](int c) { return Ac[c]; };
         auto kG = [&](int c) { return Gc[c]; };
         auto kR = [&](int c) { return R0c[c]; };
         auto kAf = [&](int d) { return AfL[d]; };
         auto kGb = [&](int d) { return GbL[d]; };
         // ================= how many levels carry anything (DESIGN.md "Truncation") =======================
-        int levels = 0;
+        // (PACK > 1: every PDE of the warp gets the level count it would get alone -- `own` -- and exact zeros as multipliers of
+        // the levels past it, so that the warp's common count `levels` changes nothing for it: a PDE's prices do not depend on
+        // which PDEs share its warp, bit for bit)
+        int levels = 0, own = 0;
         {
             const double tol = 0x1p-56 / (bmax * (double)B.tDim);
-            const double x_here = fmax(0., x_node(sc, B.density, min(lane * NODES, xDim - 1)));
+            const double x_here = fmax(0., x_node(sc, B.density, min(pl * NODES, xDim - 1)));
 #pragma unroll
             for (int d = 0; d < 5; ++d) {
-                const int src = min((lane + (1 << d)) * NODES + NODES - 1, xDim - 1);
+                const int src = min((pl + (1 << d)) * NODES + NODES - 1, xDim - 1);
                 const double growth = sc.put ? 1. : exp(fmax(0., x_node(sc, B.density, src)) - x_here);
                 const bool bad = !(fabs(AfL[d]) <= tol) || !(fabs(GbL[d]) * growth <= tol);
-                if (__any_sync(FULL, bad)) levels = d + 1;
+                const unsigned votes = __ballot_sync(FULL, bad);
+                if (votes) levels = d + 1;
+                if ((votes >> (ph * LPP)) & (0xffffffffu >> (32 - LPP))) own = d + 1;
             }
-            if (B.max_mode <= 1) levels = 5;  // FD1D.GPU.EXACT >= 1: every level
+            if (B.max_mode <= 1) levels = own = 5;  // FD1D.GPU.EXACT >= 1: every level
+            if (levels > MAXLEV) levels = MAXLEV;  // (levels past a PDE's lanes carry exact zeros)
             if (levels < 1) levels = 1;
+            if (own > MAXLEV) own = MAXLEV;
+            if (own < 1) own = 1;
+            if constexpr (PACK > 1) {
+#pragma unroll
+                for (int d = 0; d < 5; ++d)
+                    if (d >= own) AfL[d] = GbL[d] = 0.;
+            }
         }
+        // keep the multipliers as values: the compiler would otherwise re-derive the first levels from Ac[] / Gc[]
+        // inside the march loop (6 DMUL + the lane predicate per step) to save two registers
+#pragma unroll
+        for (int d = 0; d < 5; ++d) asm volatile("" : "+d"(AfL[d]), "+d"(GbL[d]));
 
         // ================= time march: fd1d_warp_kernel's SPLIT chunk-pair form ==========================
         auto march = [&](auto lev_c, auto euro_c) {
@@ -435,14 +464,14 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
                 for (int c = 1; c < NCH; ++c) S = fma(kA(c), S, e[c]);
 #pragma unroll
                 for (int d = 0; d < LEV; ++d) {
-                    const double o = __shfl_up_sync(FULL, S, 1 << d);
+                    const double o = __shfl_up_sync(FULL, S, 1 << d, LPP);
                     S = fma(kAf(d), o, S);
                 }
-                // Lane 0 has no predecessor: __shfl_up hands it its own (finite) S back.  No select is needed -- whatever
+                // A PDE's first lane has no predecessor: __shfl_up hands it its own (finite) S back.  No select is needed -- whatever
                 // Yin[0] is there, it is only ever multiplied by a~ of the grid's first node, A_0 or R0_0 of lane 0's first
                 // chunk, all exactly 0 (a~_0 = -bl_0 / beta_{-1} with 1/beta_{-1} = 0).  Likewise Uin of lane 31's last chunk
                 // below (g~ of the last node is 0).
-                Yin[0] = __shfl_up_sync(FULL, S, 1);
+                Yin[0] = __shfl_up_sync(FULL, S, 1, LPP);
 #pragma unroll
                 for (int c = 1; c < NCH; ++c) Yin[c] = fma(kA(c - 1), Yin[c - 1], e[c - 1]);
                 // backward: chunk-start values with the true forward carry, scan, chunk-exit values
@@ -453,10 +482,10 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
                 for (int c = NCH - 2; c >= 0; --c) T = fma(kG(c), T, f[c]);
 #pragma unroll
                 for (int d = 0; d < LEV; ++d) {
-                    const double o = __shfl_down_sync(FULL, T, 1 << d);
+                    const double o = __shfl_down_sync(FULL, T, 1 << d, LPP);
                     T = fma(kGb(d), o, T);
                 }
-                Uin[NCH - 1] = __shfl_down_sync(FULL, T, 1);
+                Uin[NCH - 1] = __shfl_down_sync(FULL, T, 1, LPP);
 #pragma unroll
                 for (int c = NCH - 2; c >= 0; --c) Uin[c] = fma(kG(c + 1), Uin[c + 1], f[c + 1]);
             };
@@ -612,8 +641,12 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
                 case 1: march(std::integral_constant<int, 1>{}, euro_c); break;
                 case 2: march(std::integral_constant<int, 2>{}, euro_c); break;
                 case 3: march(std::integral_constant<int, 3>{}, euro_c); break;
-                case 4: march(std::integral_constant<int, 4>{}, euro_c); break;
-                default: march(std::integral_constant<int, 5>{}, euro_c); break;
+                case 4:
+                    if constexpr (MAXLEV >= 4) march(std::integral_constant<int, 4>{}, euro_c);
+                    break;
+                default:
+                    if constexpr (MAXLEV >= 5) march(std::integral_constant<int, 5>{}, euro_c);
+                    break;
             }
         };
         // ================= epilogue: interpolate every option of this chain ===============================
@@ -625,28 +658,30 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
             Bo.prices = out;
             uint32_t q0, q1;
             chain_range(B, my_pde, q0, q1);
-            for (uint32_t q = q0 + lane; q < q1; q += 32) {
+            if (!live) q1 = q0;
+            const double* vmine = vfin + ph * XT;
+            for (uint32_t q = q0 + pl; q < q1; q += LPP) {
                 const uint32_t oi = B.csr_opt ? __ldg(B.csr_opt + q) : q;
-                price_option(Bo, oi, [&](int j) { return x_node(sc, B.density, j); }, [&](int j) { return vfin[j]; });
+                price_option(Bo, oi, [&](int j) { return x_node(sc, B.density, j); }, [&](int j) { return vmine[j]; });
             }
             __syncwarp();  // vfin is rewritten by the next emit
         };
         march_levels(std::false_type{});
-        if (lane == 0) {
-            // histogram buckets shared with Layout B: 0 = exact requested, 1 = all 5 levels, 2/3/4 = 4/3/2, 5 = 1 level
-            const int bucket = B.max_mode == 0 ? 0 : (levels == 5 ? 1 : 6 - levels);
+        if (pl == 0 && live) {
+            // histogram buckets shared with Layout B: 0 = exact requested, 1 = every level, 2/3/4 = 4/3/2, 5 = 1 level
+            const int bucket = B.max_mode == 0 ? 0 : (own == MAXLEV ? 1 : 6 - own);
             atomicAdd(&B.status[2 + bucket], 1u);
         }
         emit(B.prices);
         if constexpr (BS) {
-            if (sc.american) {
+            if (__any_sync(FULL, sc.american)) {  // (PACK > 1: a PDE given as European marches to the same values again)
                 // the European copy: payoff again (src/Pricer/kwFd1d.cpp:127-139, as in the set-up), same LU (still in
                 // tensor memory), no projection
 #pragma unroll 1
                 for (int c = 0; c < NCH; ++c) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const int j = lane * NODES + 8 * c + i;
+                        const int j = pl * NODES + 8 * c + i;
                         vfin[(8 * c + i) * 32 + lane] = j < xDim ? payoff_node_ni(sc.put, x_node_ni(sc, B.density, j)) : 0.;
                     }
                 }

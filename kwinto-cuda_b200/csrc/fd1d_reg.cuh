@@ -73,13 +73,13 @@ __device__ __forceinline__ void mat_normalise(Mat2& a)
     a.m11 *= s;
 }
 
-__device__ __forceinline__ Mat2 mat_shfl_up(const Mat2& a, int d)
+__device__ __forceinline__ Mat2 mat_shfl_up(const Mat2& a, int d, int width = 32)
 {
     Mat2 r;
-    r.m00 = __shfl_up_sync(FULL, a.m00, d);
-    r.m01 = __shfl_up_sync(FULL, a.m01, d);
-    r.m10 = __shfl_up_sync(FULL, a.m10, d);
-    r.m11 = __shfl_up_sync(FULL, a.m11, d);
+    r.m00 = __shfl_up_sync(FULL, a.m00, d, width);
+    r.m01 = __shfl_up_sync(FULL, a.m01, d, width);
+    r.m10 = __shfl_up_sync(FULL, a.m10, d, width);
+    r.m11 = __shfl_up_sync(FULL, a.m11, d, width);
     return r;
 }
 

@@ -47,8 +47,19 @@ def main():
         ("bs_2048", with_chain_members(synthetic_options(200, 26, european_every=5, call_every=3), 4, 5), 2048, 2048),
         ("bs_4096x256", with_chain_members(synthetic_options(120, 27, european_every=4, call_every=3), 4, 6), 256, 4096),
         ("bs_1500x96", with_chain_members(synthetic_options(60, 28, european_every=3, call_every=2), 3, 7), 96, 1500),
+        # x <= 256: four PDEs per warp (fd1d_iw.cuh, PACK = 4)
+        ("bs_256", with_chain_members(synthetic_options(2400, 29, european_every=5, call_every=3), 5, 8), 256, 256),
+        ("bs_200x80", with_chain_members(synthetic_options(70, 30, european_every=3, call_every=2), 3, 9), 80, 200),
     ]
+    have = {}
+    if os.path.exists(os.path.join(OUT, "bs_fused.npz")):  # cases already on file are kept (same seeds, same prices)
+        with np.load(os.path.join(OUT, "bs_fused.npz")) as z:
+            have = {k: z[k] for k in z.files}
     for key, o, t, x in cases:
+        if key + "/fd1d" in have and np.array_equal(have[key + "/options"], o):
+            for part in ("options", "grid", "fd1d_bs", "fd1d"):
+                out[key + "/" + part] = have[key + "/" + part]
+            continue
         out[key + "/options"] = o
         out[key + "/grid"] = np.array([t, x], dtype=np.int64)
         for mode, name in (("FD1D-BS", "fd1d_bs"), ("FD1D", "fd1d")):

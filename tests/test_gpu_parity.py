@@ -88,12 +88,12 @@ def test_synthetic_golden_all_shapes():
 
 @pytest.mark.parametrize("key,fused,variant", [(k, f, v) for k in ("bs_1024", "bs_700x200", "bs_513x64")
                                                for f, v in ((4, 257), (3, 252), (2, 251))] +
-                         [(k, 4, 153) for k in ("bs_512", "bs_300x100")] +
+                         [(k, 4, 158) for k in ("bs_512", "bs_300x100")] + [(k, 4, 58) for k in ("bs_256", "bs_200x80")] +
                          [("bs_2048", 4, 356), ("bs_1500x96", 4, 356), ("bs_4096x256", 4, 456)])
 def test_fd1d_bs_fused_march(key, fused, variant):
     # src/Pricer/kwFd1d_BlackScholes.cpp:15-43 with both solves of a chain marched by one launch --
-    # variant 253 (153 for 256 < x <= 512): every warp marches its chain as given, then the European copy
-    # (fd1d_warp.cuh, BS = 2);
+    # variant 257 (158 for 256 < x <= 512: two chains per warp, 58 for x <= 256: four): every warp marches its chain(s) as
+    # given, then the European copy (fd1d_iw.cuh, BS);
     # variant 252: warp w marches the chain as given, warp w + 4 its European copy (BS = 1);
     # variant 251: both in one warp's step (fd1d_warp_bs.cuh) -- against the reference's FD1D-BS prices
     # and against the two-solve path of the same library
@@ -110,7 +110,7 @@ def test_fd1d_bs_fused_march(key, fused, variant):
     assert maxdiff(got, g[key + "/fd1d_bs"]) <= TOL, maxdiff(got, g[key + "/fd1d_bs"])
     two = make_pricer(t, x, mode="FD1D-BS-GPU", **{"FD1D.GPU.BS_FUSED": 1})
     err, got2 = two.price(o)
-    assert err == "" and two.info()["variant"] not in (153, 251, 252, 253, 257)
+    assert err == "" and two.info()["variant"] not in (58, 158, 251, 252, 253, 257)
     assert maxdiff(got2, g[key + "/fd1d_bs"]) <= TOL
     assert maxdiff(got, got2) <= 1e-10
     # a plain FD1D pricer of the same configuration is unaffected
@@ -156,9 +156,9 @@ def test_fd1d_bs_fused_range_error_and_dispatch():
     # the reference's default grid with the default keys: fused from a device wave upwards
     d512 = make_pricer(mode="FD1D-BS-GPU")
     err, c = d512.price(g["bs_512/options"])
-    assert err == "" and d512.info()["variant"] == 153 and maxdiff(c, g["bs_512/fd1d_bs"]) <= TOL
-    # the fused kernels have no tile for other grids
-    bad = make_pricer(64, 256, mode="FD1D-BS-GPU", **{"FD1D.GPU.BS_FUSED": 4})
+    assert err == "" and d512.info()["variant"] == 158 and maxdiff(c, g["bs_512/fd1d_bs"]) <= TOL
+    # the fused kernels have no tile past the register layout (x > 4096: Layout A)
+    bad = make_pricer(16, 5000, mode="FD1D-BS-GPU", **{"FD1D.GPU.BS_FUSED": 4})
     err, _ = bad.price(big[:8])
     assert "BS_FUSED" in err
 
@@ -184,7 +184,7 @@ def test_all_1024_variants(variant):
     assert err == "" and maxdiff(got, g["mix_1024/fd1d"]) <= TOL
 
 
-@pytest.mark.parametrize("variant,x", [(1, 256), (2, 256), (101, 512), (102, 512), (103, 512), (133, 512), (133, 300), (136, 512), (136, 300), (137, 512), (137, 300), (237, 1024), (237, 700), (239, 1024), (239, 700), (301, 2048),
+@pytest.mark.parametrize("variant,x", [(1, 256), (2, 256), (101, 512), (102, 512), (103, 512), (133, 512), (133, 300), (138, 512), (138, 300), (38, 256), (38, 200), (38, 70), (136, 512), (136, 300), (137, 512), (137, 300), (237, 1024), (237, 700), (239, 1024), (239, 700), (301, 2048),
                                         (302, 2048), (401, 4096), (402, 4096), (331, 2048), (331, 1100), (431, 4096), (431, 3000), (336, 2048), (336, 1100), (436, 4096), (436, 3000)])
 def test_other_variants(variant, x, oracle):
     from kwfd1d.synthetic import synthetic_options
@@ -198,13 +198,40 @@ def test_other_variants(variant, x, oracle):
     assert err == "" and maxdiff(got, want) <= TOL, (variant, maxdiff(got, want))
 
 
+@pytest.mark.parametrize("variant,x", [(138, 512), (138, 257), (38, 256), (38, 129)])
+def test_packed_warps(variant, x, oracle):
+    """Two / four PDEs per warp (fd1d_iw.cuh, PACK): PDE counts that leave the last work unit short, American and European
+    and put and call chains side by side in one warp, and a chain of garbage (NaN volatility) next to good ones -- every PDE
+    is priced as if it were alone (bit-identical to the CTA-per-PDE kernel's neighbours-free answer is not required: the
+    oracle is the bar), and nothing crosses from the NaN chain into its warp-mates."""
+    from kwfd1d.synthetic import synthetic_options
+
+    t = 64
+    for n in (1, 2, 3, 5, 37):
+        o = synthetic_options(n, 300 + n, european_every=2, call_every=3)
+        want, oerr = oracle.fd1d(o, t, x)
+        assert oerr == ""
+        p = make_pricer(t, x, **{"FD1D.GPU.VARIANT": variant, "FD1D.GPU.COMPRESS": 0})
+        err, got = p.price(o)
+        assert err == "" and maxdiff(got, want) <= TOL, (variant, n, maxdiff(got, want))
+        assert p.info()["variant"] == variant and p.info()["last_n_pde"] == n
+    o = synthetic_options(16, 9, european_every=3, call_every=2)
+    want, _ = oracle.fd1d(o, t, x)
+    bad = o.copy()
+    bad["z"][5] = np.nan
+    p = make_pricer(t, x, **{"FD1D.GPU.VARIANT": variant, "FD1D.GPU.COMPRESS": 0})
+    err, got = p.price(bad)
+    keep = np.arange(16) != 5
+    assert np.isnan(got[5]) and maxdiff(got[keep], want[keep]) <= TOL, (err, got)
+
+
 def test_device_side_compression_matches_host_side():
     """FD1D.GPU.COMPRESS = 1 groups the chains with a hash join in HBM (compress.cuh), 2 on the host (the
     reference's sort, src/Pricer/kwFd1d.cpp:28-65, replaced by a hash map), 0 not at all: same prices,
     bit for bit, and the same number of PDEs as the reference finds (600 chains in the fixture)."""
     g = load_golden("portfolio_fd1d")
     o = g["options"]
-    for variant in (101, 133):  # the kernel is pinned: the auto dispatch picks it from the PDE count
+    for variant in (101, 138):  # the kernel is pinned: the auto dispatch picks it from the PDE count
         res = {}
         for c in (0, 1, 2):
             p = make_pricer(128, 512, **{"FD1D.GPU.COMPRESS": c, "FD1D.GPU.VARIANT": variant})
@@ -275,8 +302,9 @@ def test_wide_layout_w(x, t, n, oracle):
 def test_compression_and_permutation_are_bit_neutral():
     g = load_golden("portfolio_fd1d")
     o = g["options"]
-    a = make_pricer(256, 512, **{"FD1D.GPU.VARIANT": 133})  # same kernel on both sides (auto picks by PDE count)
-    b = make_pricer(256, 512, **{"FD1D.GPU.COMPRESS": 0, "FD1D.GPU.VARIANT": 133})
+    a = make_pricer(256, 512, **{"FD1D.GPU.VARIANT": 138})  # same kernel on both sides (auto picks by PDE count); two PDEs
+    # per warp: a chain's prices must not depend on which chain shares its warp
+    b = make_pricer(256, 512, **{"FD1D.GPU.COMPRESS": 0, "FD1D.GPU.VARIANT": 138})
     _, pa = a.price(o)
     _, pb = b.price(o[:1500])
     assert a.info()["last_n_pde"] == 600 and b.info()["last_n_pde"] == 1500
