@@ -363,6 +363,7 @@ struct kw_fd1d_handle {
     int regs_bs = 0;
     bool bs_forced = false;                 // FD1D.GPU.BS_FUSED = 2 / 3: fused for every batch size
     const RegVariant* last_var = nullptr;   // what the last batch ran
+    uint32_t class_split = 0;               // != 0: the last batch launched var_small AND var; chains < class_split ran var_small
     int last_grid = 0;
     int launches = 0;  // kernels launched by the current / last price call
     uint64_t last_n_pde = 0;
@@ -430,6 +431,8 @@ int launch_batch(kw_fd1d_handle* h, Fd1dBatch B, cudaStream_t st)
 {
     for (int i = 0; i < 4; ++i) B.opq_lim[i] = INT32_MAX;
     B.opq_zero = 0;
+    B.pde_lo = 0;
+    B.pde_hi = 0xffffffffu;
     B.work_counter = B.status + 8;
     status_reset_kernel<<<1, 1, 0, st>>>(B.status, h->unsynced ? 1 : 0);
     h->unsynced = true;
@@ -438,42 +441,59 @@ int launch_batch(kw_fd1d_handle* h, Fd1dBatch B, cudaStream_t st)
     if (h->layout == KW_FD1D_LAYOUT_REG) {
         const bool fused = B.prices_eu != nullptr;
         if (fused && !h->var_bs) return fail(h, KW_FD1D_EINVAL, "Fd1dGpu_Pricer::price: no fused FD1D-BS kernel for this configuration");
-        const bool small = !fused && h->var_small && B.n_pde < h->small_below;
-        const RegVariant* v = fused ? h->var_bs : (small ? h->var_small : h->var);
-        h->last_var = v;
-        int grid = h->sm_count * (fused ? h->ctas_per_sm_bs : (small ? h->ctas_per_sm_small : h->ctas_per_sm));
-        const uint32_t ppc = v->pdes_per_cta > 1 ? (uint32_t)v->pdes_per_cta : 1u;
-        const uint32_t want = (B.n_pde + ppc - 1) / ppc;  // with device-side compression n_pde = n is an upper bound
-        if ((uint32_t)grid > want) grid = (int)want;
-        h->last_grid = grid;
-        if (v->wide_nwp) {
-            // set-up kernel -> HBM workspace -> march kernel, one chunk of the batch at a time
-            // chunk = as many PDEs as fit a 2 GiB workspace (a multiple of one wave of the march grid)
-            const uint32_t wave = (uint32_t)(h->sm_count * h->ctas_per_sm) * ppc;
-            uint32_t fit = (uint32_t)(((size_t)2 << 30) / (v->slot_doubles * sizeof(double)));
-            fit = std::max(wave, fit / wave * wave);
-            const uint32_t cap = std::min<uint32_t>(B.n_pde, fit);
-            KW_CUDA(h, h->d_ws.reserve((size_t)cap * v->slot_doubles));
-            KW_CUDA(h, cudaEventRecord(h->ev0, st));
-            const int P = 128 * v->wide_nwp;
-            for (uint32_t base = 0; base < B.n_pde; base += cap) {
-                const uint32_t cnt = std::min<uint32_t>(cap, B.n_pde - base);
-                const int gs = (int)std::min<uint32_t>(cnt, (uint32_t)(h->sm_count * (2048 / P)));
-                v->setup_fn<<<gs, P, v->setup_smem, st>>>(B, h->d_ws.p, base, cnt, v->icmp);
-                const uint32_t wantc = (cnt + ppc - 1) / ppc;
-                const int gm = (int)std::min<uint32_t>(wantc, (uint32_t)(h->sm_count * h->ctas_per_sm));
-                v->wide_fn<<<gm, 128, v->smem, st>>>(B, h->d_ws.p, base, cnt);
-                h->launches += 2;
-                h->last_grid = gm;
+        // one variant over the batch `Bx` (its PDE-count class [pde_lo, pde_hi) decides on the device whether it runs at all)
+        auto run = [&](const RegVariant* v, int ctas_per_sm, const Fd1dBatch& Bx, uint32_t n_max) -> cudaError_t {
+            const uint32_t ppc = v->pdes_per_cta > 1 ? (uint32_t)v->pdes_per_cta : 1u;
+            if (v->wide_nwp) {
+                // set-up kernel -> HBM workspace -> march kernel, one chunk of the batch at a time
+                // chunk = as many PDEs as fit a 2 GiB workspace (a multiple of one wave of the march grid)
+                const uint32_t wave = (uint32_t)(h->sm_count * ctas_per_sm) * ppc;
+                uint32_t fit = (uint32_t)(((size_t)2 << 30) / (v->slot_doubles * sizeof(double)));
+                fit = std::max(wave, fit / wave * wave);
+                const uint32_t cap = std::min<uint32_t>(n_max, fit);
+                if (cudaError_t e = h->d_ws.reserve((size_t)cap * v->slot_doubles)) return e;
+                const int P = 128 * v->wide_nwp;
+                for (uint32_t base = 0; base < n_max; base += cap) {
+                    const uint32_t cnt = std::min<uint32_t>(cap, n_max - base);
+                    const int gs = (int)std::min<uint32_t>(cnt, (uint32_t)(h->sm_count * (2048 / P)));
+                    v->setup_fn<<<gs, P, v->setup_smem, st>>>(Bx, h->d_ws.p, base, cnt, v->icmp);
+                    const uint32_t wantc = (cnt + ppc - 1) / ppc;
+                    const int gm = (int)std::min<uint32_t>(wantc, (uint32_t)(h->sm_count * ctas_per_sm));
+                    v->wide_fn<<<gm, 128, v->smem, st>>>(Bx, h->d_ws.p, base, cnt);
+                    h->launches += 2;
+                    h->last_grid = gm;
+                }
+                return cudaSuccess;
             }
-            KW_CUDA(h, cudaEventRecord(h->ev1, st));
-            h->ev_valid = true;
-            KW_CUDA(h, cudaGetLastError());
-            return KW_FD1D_OK;
-        }
+            int grid = h->sm_count * ctas_per_sm;
+            const uint32_t want = (n_max + ppc - 1) / ppc;
+            if ((uint32_t)grid > want) grid = (int)want;
+            h->last_grid = grid;
+            v->fn<<<grid, v->pdes_per_cta > 1 ? std::max(128, v->P) : v->P, v->smem, st>>>(Bx);
+            h->launches += 1;
+            return cudaSuccess;
+        };
         KW_CUDA(h, cudaEventRecord(h->ev0, st));
-        v->fn<<<grid, v->pdes_per_cta > 1 ? std::max(128, v->P) : v->P, v->smem, st>>>(B);
-        h->launches += 1;
+        h->class_split = 0;
+        if (!fused && h->var_small && B.n_pde_dev && B.n_pde >= h->small_below) {
+            // Device-side chain compression: B.n_pde is the OPTION count, the number of chains is known only on the device, and the
+            // dispatch is by chains (a portfolio of 6000 options in 600 chains belongs to the small-batch kernel).  Reading the
+            // count back would cost a stream synchronisation in the middle of an asynchronous call; instead BOTH kernels are
+            // launched and each returns at once unless the count falls into its class (batch_n_pde(), fd1d_common.cuh): an
+            // idle launch costs 2-3 us.  kw_fd1d_sync reports which one ran.
+            Fd1dBatch Bs = B, Bb = B;
+            Bs.pde_hi = h->small_below;
+            Bb.pde_lo = h->small_below;
+            KW_CUDA(h, run(h->var_small, h->ctas_per_sm_small, Bs, h->small_below - 1));
+            KW_CUDA(h, run(h->var, h->ctas_per_sm, Bb, B.n_pde));
+            h->class_split = h->small_below;
+            h->last_var = h->var;
+        } else {
+            const bool small = !fused && h->var_small && B.n_pde < h->small_below;
+            const RegVariant* v = fused ? h->var_bs : (small ? h->var_small : h->var);
+            h->last_var = v;
+            KW_CUDA(h, run(v, fused ? h->ctas_per_sm_bs : (small ? h->ctas_per_sm_small : h->ctas_per_sm), B, B.n_pde));
+        }
         KW_CUDA(h, cudaEventRecord(h->ev1, st));
         h->ev_valid = true;
         KW_CUDA(h, cudaGetLastError());
@@ -677,6 +697,7 @@ int check_status(kw_fd1d_handle* h, cudaStream_t st, const kw_option* host_asset
         uint64_t m = 0;
         for (int i = 0; i < 6; ++i) m += h->mode_count[i];
         h->last_n_pde = m;
+        if (h->class_split) h->last_var = m < h->class_split ? h->var_small : h->var;
     }
     if (h->h_status.p[0] != 0) {
         const unsigned int idx = h->h_status.p[1];

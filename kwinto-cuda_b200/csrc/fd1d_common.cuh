@@ -49,11 +49,15 @@ struct Fd1dBatch {
     uint32_t opq_zero;
     // fd1d_iw.cuh: the next PDE to hand out (status[8], zeroed by status_reset_kernel before every launch)
     unsigned int* work_counter;
+    // PDE-count class of this launch: with the count known only on the device (n_pde_dev), capi.cu launches the kernel of
+    // every class and the ones whose class [pde_lo, pde_hi) does not hold the count see an empty batch
+    uint32_t pde_lo, pde_hi;
 };
 
 __device__ __forceinline__ uint32_t batch_n_pde(const Fd1dBatch& B)
 {
-    return B.n_pde_dev ? __ldg(B.n_pde_dev) : B.n_pde;
+    const uint32_t n = B.n_pde_dev ? __ldg(B.n_pde_dev) : B.n_pde;
+    return (n >= B.pde_lo && n < B.pde_hi) ? n : 0u;
 }
 
 // [q0, q1) = this PDE's entries of csr_opt

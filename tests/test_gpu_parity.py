@@ -246,8 +246,15 @@ def test_device_side_compression_matches_host_side():
     big = base[rng.integers(0, 600, size=50000)]
     big["k"] = rng.uniform(60., 140., size=big.shape[0])
     big["s"] = 100.
+    for variant in (1, 38):  # pinned: the auto dispatch would pick by chain count (600 / 50000), see the next test
+        a = make_pricer(64, 256, **{"FD1D.GPU.COMPRESS": 1, "FD1D.GPU.VARIANT": variant})
+        b = make_pricer(64, 256, **{"FD1D.GPU.COMPRESS": 0, "FD1D.GPU.VARIANT": variant})
+        err, pa = a.price(big)
+        assert err == "" and a.info()["last_n_pde"] == len(np.unique(big[["t", "r", "q", "z", "e", "w"]]))
+        err, pb = b.price(big)
+        assert err == "" and np.array_equal(pa, pb), variant
     a = make_pricer(64, 256, **{"FD1D.GPU.COMPRESS": 1})
-    b = make_pricer(64, 256, **{"FD1D.GPU.COMPRESS": 0})
+    b = make_pricer(64, 256, **{"FD1D.GPU.COMPRESS": 2})
     err, pa = a.price(big)
     assert err == "" and a.info()["last_n_pde"] == len(np.unique(big[["t", "r", "q", "z", "e", "w"]]))
     err, pb = b.price(big)
@@ -297,6 +304,33 @@ def test_wide_layout_w(x, t, n, oracle):
         assert maxdiff(got, want) <= TOL, (x, t, exact, maxdiff(got, want))
     print("wide", x, t, "exact-vs-auto", maxdiff(res[0], res[2]), "vs oracle", maxdiff(res[0], want))
     assert maxdiff(res[0], res[2]) <= 1e-11
+
+
+def test_dispatch_goes_by_chains_not_options():
+    """With device-side chain compression the chain count is known only on the device: the kernels of both batch-size classes
+    are launched and the count picks the one that runs (capi.cu launch_batch, fd1d_common.cuh batch_n_pde).  The fixture's
+    6000 options are 600 chains: the small-batch kernel prices them, although 6000 PDEs would go to Layout W."""
+    g = load_golden("portfolio_fd1d")
+    o = g["options"]
+    for x, small, big in ((512, 101, 138), (1024, 201, 237), (256, 1, 38)):
+        p = make_pricer(64, x)
+        err, a = p.price(o)
+        assert err == "" and p.info()["last_n_pde"] == 600 and p.info()["variant"] == small, p.info()
+        q = make_pricer(64, x, **{"FD1D.GPU.COMPRESS": 0})
+        err, b = q.price(o)
+        assert err == "" and q.info()["last_n_pde"] == 6000 and q.info()["variant"] == big, q.info()
+        r = make_pricer(64, x, **{"FD1D.GPU.COMPRESS": 2})  # host-side compression knows the count before the launch
+        err, c = r.price(o)
+        assert err == "" and r.info()["variant"] == small and np.array_equal(a, c)
+        assert maxdiff(a, b) <= 1e-11
+        # a batch of many chains on the same handle afterwards takes the other class
+        from kwfd1d.synthetic import synthetic_options
+
+        many = synthetic_options(4000, 11)
+        err, d = p.price(many)
+        assert err == "" and p.info()["variant"] == big and p.info()["last_n_pde"] == 4000
+        err, e = q.price(many)
+        assert err == "" and np.array_equal(d, e)
 
 
 def test_compression_and_permutation_are_bit_neutral():
