@@ -92,6 +92,11 @@ struct RegVariant {
         ID, KW_FD1D_F64, 8, 128 / PACK_, 2, false, false, fd1d_iw_kernel<4, 2, false, false, PACK_>, \
             IwSmem<4>::bytes(), 256, 4 * PACK_                                                     \
     }
+#define KW_VARIANT_IWF(ID, PACK_)                                                                 \
+    {                                                                                              \
+        ID, KW_FD1D_F32, 8, 128 / PACK_, 2, false, false, fd1d_iw_kernel<4, 2, false, false, PACK_, float>, \
+            IwSmem<4>::bytes(), 256, 4 * PACK_                                                     \
+    }
 #define KW_VARIANT_WRT(ID, MINB_)                                                                 \
     {                                                                                              \
         ID, KW_FD1D_F64, 8, 128, MINB_, false, false, fd1d_warp_kernel<4, MINB_, false, true, 0, true>, \
@@ -146,9 +151,13 @@ const RegVariant g_variants[] = {
     KW_VARIANT_WIDES(436, 4),                  // x <= 4096: Layout W over four warps per PDE, rotated split march (31.3 vs 36.0 ms)
     KW_VARIANT(401, 8, 512, 1, true, true),    // x <= 4096, CTA per PDE (small batches)
     // fp32 march (fp64 set-up): FD1D.GPU.PRECISION = f32
+    // Layout W: the independent-warp kernel with a float march, every coefficient of the lane in registers (fd1d_iw.cuh, RC):
+    // 1024^2 12.55 ms against 14.9 ms for round 1's 1233, 512^2 3.73 against 4.51 ms (1101), 256^2 1.01 against 1.35 ms (1001)
+    KW_VARIANT_IWF(1038, 4),     // x <= 256, four PDEs per warp
     KW_VARIANT_F32(1001, 8, 32, 16),
+    KW_VARIANT_IWF(1138, 2),     // x <= 512, two PDEs per warp
     KW_VARIANT_F32(1101, 8, 64, 8),
-    KW_VARIANT_WF(1233, 4, 2),   // Layout W, float march, 512 < x <= 1024
+    KW_VARIANT_IWF(1237, 1),     // x <= 1024
     KW_VARIANT_F32(1201, 8, 128, 4),
     KW_VARIANT_F32(1301, 8, 256, 2),
     KW_VARIANT_F32(1401, 8, 512, 1),
@@ -182,6 +191,7 @@ const RegVariant g_variants[] = {
     KW_VARIANT(302, 8, 256, 2, true, true),
     KW_VARIANT_WIDE(431, 4, false),            // the round-1 four-warp kernel
     KW_VARIANT(402, 8, 512, 1, true, false),
+    KW_VARIANT_WF(1233, 4, 2),   // round 1's Layout W with a float march, 512 < x <= 1024 (CTA-cooperative set-up, coefficients in tensor memory)
     KW_VARIANT_WF(1133, 2, 2),   // Layout W, float march, 256 < x <= 512 (slower than 1101: 6.0 M vs 7.1 M options/s)
 #endif
 };

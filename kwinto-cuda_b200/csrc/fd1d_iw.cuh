@@ -60,11 +60,21 @@ struct IwSmem {
 // (nothing, not even a NaN, crosses over).  The step then costs what a full-tile PDE's step costs and advances PACK PDEs: the
 // 512-node grid runs at the instruction mix of the 1024-node kernel (4 chunks per lane, two chunk pairs, rotated loop) instead of
 // the single-pair loop of NCH = 2, whose scans have no sweeps to hide behind.
-template <int NCH, int MINB, bool BS = false, bool D4 = false, int PACK = 1>
+// F: arithmetic type of the march -- double, or float for FD1D.GPU.PRECISION = f32 (the set-up, the scan multipliers and the level
+// test stay in fp64; a~, g~, D, the floor and v are rounded once, when the march takes them over; 8 instead of 16 tensor-memory
+// columns per 8-value block, written over the parked fp64 rows chunk by chunk, always behind the reads).
+template <int NCH, int MINB, bool BS = false, bool D4 = false, int PACK = 1, class F = double>
 __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
 {
     static_assert(NCH == 4 || NCH == 2, "4 chunks per lane (512 < x <= 1024) or 2 (256 < x <= 512)");
     static_assert(PACK == 1 || PACK == 2 || PACK == 4, "1, 2 or 4 PDEs per warp");
+    constexpr bool F64 = std::is_same<F, double>::value;
+    static_assert(F64 || !D4, "the half-chunk lookahead exists in fp64 only");
+    constexpr int CW = F64 ? 16 : 8;  // tensor-memory columns of an 8-value block of the march
+    // fp32: a~, g~, D and the floor of the lane's 32 nodes are 128 registers -- with v (32) and the scan constants they fit the
+    // register file, so the march loads them from tensor memory ONCE per PDE and its loop touches no memory at all; one basic
+    // block per step, the compiler interleaves the sweeps of both chunk pairs (four dependent chains per warp)
+    constexpr bool RC = !F64;
     constexpr int N = IwSmem<NCH>::N;
     constexpr int NODES = 8 * NCH;  // per lane
     constexpr int LPP = 32 / PACK;  // lanes per PDE
@@ -105,7 +115,7 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
         const kw_option opt = load_option(B.opts + rep);
         const PdeScalars sc = pde_scalars(opt, B);
 
-        double vr[NODES];
+        F vr[NODES];
         double Ac[NCH], Gc[NCH], R0c[NCH];
         double bmax = 0.;
         // ================= set-up (setup_lu of fd1d_reg.cuh, one warp, NCH chunks per lane) ==============
@@ -132,7 +142,8 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
 #pragma unroll
                     for (int i = 1; i <= 8; ++i) xl[1 + i] = x_node_ni(sc, B.density, j0 + 8 * c + i);
                     if (pl == LPP - 1 && c == NCH - 1) xl[9] = xl[8];  // past the tile: the last node again
-                    double t8[8], bl[8], bb[8], bu[8];
+                    F t8[8];
+                    double bl[8], bb[8], bu[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int j = j0 + 8 * c + i;
@@ -140,10 +151,10 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
                         if (j < xDim) p = payoff_node_ni(sc.put, xl[1 + i]);
                         s_v[(8 * c + i) * 32 + lane] = p;
                         // projection skips the last node (src/Math/kwFd1d.cpp:130); European: never
-                        t8[i] = (sc.american && j < xDim - 1) ? p : -CUDART_INF;
+                        t8[i] = (sc.american && j < xDim - 1) ? (F)p : (F)-CUDART_INF;
                         b_row(sc, j, xDim, xl[i], xl[1 + i], xl[2 + i], bl[i], bb[i], bu[i]);
                     }
-                    tmem::st8(tbase + T_P + 16 * c, t8);
+                    tmem::st8(tbase + T_P + CW * c, t8);
                     tmem::st8(tbase + T_A + 16 * c, bl);
                     tmem::st8(tbase + T_G + 16 * c, bb);
                     tmem::st8(tbase + T_D + 16 * c, bu);
@@ -283,9 +294,25 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
                         g[i] = -bu[i] * (i < 7 ? ib[i < 7 ? i + 1 : i] : ib_next);
                         D[i] = j < xDim ? 2. * ib[i] : 0.;
                     }
-                    tmem::st8(tbase + T_A + 16 * c, a);
-                    tmem::st8(tbase + T_G + 16 * c, g);
-                    tmem::st8(tbase + T_D + 16 * c, D);
+                    if constexpr (F64) {
+                        tmem::st8(tbase + T_A + 16 * c, a);
+                        tmem::st8(tbase + T_G + 16 * c, g);
+                        tmem::st8(tbase + T_D + 16 * c, D);
+                    } else {
+                        // 8 columns per block, over the first half of the fp64 rows that iteration c / 2 has consumed
+                        // (8 c + 8 <= 16 c for c >= 1; c = 0: its own rows, already in registers); the next chunk's 1/beta
+                        // at 16 (c + 1) is still ahead of the write
+                        F af[8], gf[8], Df[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            af[i] = (F)a[i];
+                            gf[i] = (F)g[i];
+                            Df[i] = (F)D[i];
+                        }
+                        tmem::st8(tbase + T_A + CW * c, af);
+                        tmem::st8(tbase + T_G + CW * c, gf);
+                        tmem::st8(tbase + T_D + CW * c, Df);
+                    }
                     // chunk scalars: A = prod a~, G = prod g~, R0 = d(u~_first)/d(Yin) (backward sweep of the prefix products)
                     double Pp[8];
                     Pp[0] = a[0];
@@ -330,7 +357,7 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
                 R0c[c] = s_k[(3 * c + 2) * 32 + lane];
             }
 #pragma unroll
-            for (int i = 0; i < NODES; ++i) vr[i] = s_v[i * 32 + lane];
+            for (int i = 0; i < NODES; ++i) vr[i] = (F)s_v[i * 32 + lane];
             __syncwarp();  // the scratch is the final-v stage later
         }
 
@@ -360,18 +387,19 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
                 if (pl < LPP - s) G *= o;
             }
         }
-        auto kA = [&](int c) { return Ac[c]; };
-        auto kG = [&](int c) { return Gc[c]; };
-        auto kR = [&](int c) { return R0c[c]; };
-        auto kAf = [&](int d) { return AfL[d]; };
-        auto kGb = [&](int d) { return GbL[d]; };
+        F AcF[NCH], GcF[NCH], R0F[NCH], AfF[5], GbF[5];  // the march's copies (fp64: the same registers), filled below
+        auto kA = [&](int c) { return AcF[c]; };
+        auto kG = [&](int c) { return GcF[c]; };
+        auto kR = [&](int c) { return R0F[c]; };
+        auto kAf = [&](int d) { return AfF[d]; };
+        auto kGb = [&](int d) { return GbF[d]; };
         // ================= how many levels carry anything (DESIGN.md "Truncation") =======================
         // (PACK > 1: every PDE of the warp gets the level count it would get alone -- `own` -- and exact zeros as multipliers of
         // the levels past it, so that the warp's common count `levels` changes nothing for it: a PDE's prices do not depend on
         // which PDEs share its warp, bit for bit)
         int levels = 0, own = 0;
         {
-            const double tol = 0x1p-56 / (bmax * (double)B.tDim);
+            const double tol = (F64 ? 0x1p-56 : 0x1p-30) / (bmax * (double)B.tDim);
             const double x_here = fmax(0., x_node(sc, B.density, min(pl * NODES, xDim - 1)));
 #pragma unroll
             for (int d = 0; d < 5; ++d) {
@@ -396,13 +424,24 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
         // keep the multipliers as values: the compiler would otherwise re-derive the first levels from Ac[] / Gc[]
         // inside the march loop (6 DMUL + the lane predicate per step) to save two registers
 #pragma unroll
-        for (int d = 0; d < 5; ++d) asm volatile("" : "+d"(AfL[d]), "+d"(GbL[d]));
+        for (int c = 0; c < NCH; ++c) {
+            AcF[c] = (F)Ac[c];
+            GcF[c] = (F)Gc[c];
+            R0F[c] = (F)R0c[c];
+        }
+#pragma unroll
+        for (int d = 0; d < 5; ++d) {
+            AfF[d] = (F)AfL[d];
+            GbF[d] = (F)GbL[d];
+            if constexpr (F64) asm volatile("" : "+d"(AfF[d]), "+d"(GbF[d]));
+            else asm volatile("" : "+f"(AfF[d]), "+f"(GbF[d]));
+        }
 
         // ================= time march: fd1d_warp_kernel's SPLIT chunk-pair form ==========================
         auto march = [&](auto lev_c, auto euro_c) {
             constexpr int LEV = decltype(lev_c)::value;
             constexpr bool EURO = decltype(euro_c)::value;  // European copy: no floor, no compare
-            double e[NCH], f[NCH];
+            F e[NCH], f[NCH];
             // D4: half-chunk constants and carried half-chunk values in the warp's scratch, [row][lane]
             const uint32_t a_h = smem_addr(scr + lane);
             auto hP_lo = [&](int c) { return lds_f64(a_h + (5 * c + 0) * 256); };
@@ -415,14 +454,14 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
             auto st_e3 = [&](int c, double v) { sts_f64(a_h + (20 + c) * 256, v); };
             auto st_l4 = [&](int c, double v) { sts_f64(a_h + (24 + c) * 256, v); };
             // local sweeps of chunk c from zero (next step's aggregates): e = last forward value, f = first backward value
-            auto local_chunk = [&](int c, const double (&a8)[8], const double (&g8)[8]) {
+            auto local_chunk = [&](int c, const F (&a8)[8], const F (&g8)[8]) {
                 if constexpr (!D4) {
-                    double y[8];
+                    F y[8];
                     y[0] = vr[8 * c];
 #pragma unroll
                     for (int i = 1; i < 8; ++i) y[i] = fma(a8[i], y[i - 1], vr[8 * c + i]);
                     e[c] = y[7];
-                    double u = y[7];
+                    F u = y[7];
 #pragma unroll
                     for (int i = 6; i >= 0; --i) u = fma(g8[i], u, y[i]);
                     f[c] = u;
@@ -450,21 +489,41 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
             };
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
-                double a8[8], g8[8];
-                tmem::ld8(tbase + T_A + 16 * c, a8);
-                tmem::ld8(tbase + T_G + 16 * c, g8);
+                F a8[8], g8[8];
+                tmem::ld8(tbase + T_A + CW * c, a8);
+                tmem::ld8(tbase + T_G + CW * c, g8);
                 tmem::wait_ld_dep(a8, g8);
                 local_chunk(c, a8, g8);
             }
-            double Yin[NCH], Uin[NCH];
+            F aR[RC ? NODES : 1], gR[RC ? NODES : 1], dR[RC ? NODES : 1], pR[RC ? NODES : 1];
+            if constexpr (RC) {
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    F t0[8], t1[8], t2[8], t3[8];
+                    tmem::ld8(tbase + T_A + CW * c, t0);
+                    tmem::ld8(tbase + T_G + CW * c, t1);
+                    tmem::ld8(tbase + T_D + CW * c, t2);
+                    tmem::ld8(tbase + T_P + CW * c, t3);
+                    tmem::wait_ld_dep(t0, t1);
+                    tmem::wait_ld_dep(t2, t3);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        aR[8 * c + i] = t0[i];
+                        gR[8 * c + i] = t1[i];
+                        dR[8 * c + i] = t2[i];
+                        pR[8 * c + i] = t3[i];
+                    }
+                }
+            }
+            F Yin[NCH], Uin[NCH];
             // ---- the scans of one step: lane aggregates, Kogge-Stone over the lanes, chunk-entry / -exit values
             auto scan = [&]() {
-                double S = e[0];
+                F S = e[0];
 #pragma unroll
                 for (int c = 1; c < NCH; ++c) S = fma(kA(c), S, e[c]);
 #pragma unroll
                 for (int d = 0; d < LEV; ++d) {
-                    const double o = __shfl_up_sync(FULL, S, 1 << d, LPP);
+                    const F o = __shfl_up_sync(FULL, S, 1 << d, LPP);
                     S = fma(kAf(d), o, S);
                 }
                 // A PDE's first lane has no predecessor: __shfl_up hands it its own (finite) S back.  No select is needed -- whatever
@@ -477,12 +536,12 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
                 // backward: chunk-start values with the true forward carry, scan, chunk-exit values
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) f[c] = fma(kR(c), Yin[c], f[c]);
-                double T = f[NCH - 1];
+                F T = f[NCH - 1];
 #pragma unroll
                 for (int c = NCH - 2; c >= 0; --c) T = fma(kG(c), T, f[c]);
 #pragma unroll
                 for (int d = 0; d < LEV; ++d) {
-                    const double o = __shfl_down_sync(FULL, T, 1 << d, LPP);
+                    const F o = __shfl_down_sync(FULL, T, 1 << d, LPP);
                     T = fma(kGb(d), o, T);
                 }
                 Uin[NCH - 1] = __shfl_down_sync(FULL, T, 1, LPP);
@@ -491,11 +550,19 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
             };
             // ---- true forward sweeps of the chunk pair (cA, cA + 1) from Yin
             // (D4: y3[0], y3[1] = the lookahead values y_3* of the two chunks, needed again by the backward lookahead)
-            auto fwd_pair = [&](int cA, double (&yA)[8], double (&yB)[8], double (&y3)[2]) {
+            auto fwd_pair = [&](int cA, F (&yA)[8], F (&yB)[8], F (&y3)[2]) {
                 const int cB = cA + 1;
-                double aA[8], aB[8];
-                tmem::ld16(tbase + T_A + 16 * cA, aA, aB);
-                tmem::hot_wait(aA, aB);
+                F aA[8], aB[8];
+                if constexpr (RC) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        aA[i] = aR[8 * cA + i];
+                        aB[i] = aR[8 * cB + i];
+                    }
+                } else {
+                    tmem::ld16(tbase + T_A + CW * cA, aA, aB);
+                    tmem::hot_wait(aA, aB);
+                }
                 if constexpr (!D4) {
                     yA[0] = fma(aA[0], Yin[cA], vr[8 * cA]);
                     yB[0] = fma(aB[0], Yin[cB], vr[8 * cB]);
@@ -521,24 +588,36 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
                 }
             };
             // ---- true backward sweeps from Uin, projection, next step's local sweeps (a~, g~ loaded again)
-            auto back_pair = [&](int cA, double (&yA)[8], double (&yB)[8], const double (&y3)[2]) {
+            auto back_pair = [&](int cA, F (&yA)[8], F (&yB)[8], const F (&y3)[2]) {
                 const int cB = cA + 1;
-                double gA[8], gB[8], dA[8], dB[8], pA[8], pB[8];
-                tmem::ld16(tbase + T_G + 16 * cA, gA, gB);
-                tmem::ld16(tbase + T_D + 16 * cA, dA, dB);
-                if constexpr (!EURO) {
-                    tmem::ld16(tbase + T_P + 16 * cA, pA, pB);
-                    tmem::hot_wait(gA, gB, dA);
-                    tmem::hot_wait(dB, pA, pB);
+                F gA[8], gB[8], dA[8], dB[8], pA[8], pB[8];
+                if constexpr (RC) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        gA[i] = gR[8 * cA + i];
+                        gB[i] = gR[8 * cB + i];
+                        dA[i] = dR[8 * cA + i];
+                        dB[i] = dR[8 * cB + i];
+                        pA[i] = pR[8 * cA + i];
+                        pB[i] = pR[8 * cB + i];
+                    }
                 } else {
-                    tmem::hot_wait(gA, gB);
-                    tmem::hot_wait(dA, dB);
+                    tmem::ld16(tbase + T_G + CW * cA, gA, gB);
+                    tmem::ld16(tbase + T_D + CW * cA, dA, dB);
+                    if constexpr (!EURO) {
+                        tmem::ld16(tbase + T_P + CW * cA, pA, pB);
+                        tmem::hot_wait(gA, gB, dA);
+                        tmem::hot_wait(dB, pA, pB);
+                    } else {
+                        tmem::hot_wait(gA, gB);
+                        tmem::hot_wait(dA, dB);
+                    }
                 }
-                auto node = [&](int i, double& uA, double& uB) {
+                auto node = [&](int i, F& uA, F& uB) {
                     uA = fma(gA[i], uA, yA[i]);
                     uB = fma(gB[i], uB, yB[i]);
-                    const double rA = fma(dA[i], uA, -vr[8 * cA + i]);
-                    const double rB = fma(dB[i], uB, -vr[8 * cB + i]);
+                    const F rA = fma(dA[i], uA, -vr[8 * cA + i]);
+                    const F rB = fma(dB[i], uB, -vr[8 * cB + i]);
                     if constexpr (EURO) {
                         vr[8 * cA + i] = rA;
                         vr[8 * cB + i] = rB;
@@ -548,7 +627,7 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
                     }
                 };
                 if constexpr (!D4) {
-                    double uA = Uin[cA], uB = Uin[cB];
+                    F uA = Uin[cA], uB = Uin[cB];
 #pragma unroll
                     for (int i = 7; i >= 0; --i) node(i, uA, uB);
                 } else {
@@ -561,11 +640,19 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
                         node(i, ulA, ulB);
                     }
                 }
-                double aA[8], aB[8];
-                tmem::ld16(tbase2 + T_A + 16 * cA, aA, aB);
-                tmem::ld16(tbase2 + T_G + 16 * cA, gA, gB);
-                tmem::hot_wait(aA, aB);
-                tmem::hot_wait(gA, gB);
+                F aA[8], aB[8];
+                if constexpr (RC) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        aA[i] = aR[8 * cA + i];
+                        aB[i] = aR[8 * cB + i];
+                    }
+                } else {
+                    tmem::ld16(tbase2 + T_A + CW * cA, aA, aB);
+                    tmem::ld16(tbase2 + T_G + CW * cA, gA, gB);
+                    tmem::hot_wait(aA, aB);
+                    tmem::hot_wait(gA, gB);
+                }
                 if constexpr (!D4) {
                     yA[0] = vr[8 * cA];
                     yB[0] = vr[8 * cB];
@@ -576,7 +663,7 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
                     }
                     e[cA] = yA[7];
                     e[cB] = yB[7];
-                    double uA = yA[7], uB = yB[7];
+                    F uA = yA[7], uB = yB[7];
 #pragma unroll
                     for (int i = 6; i >= 0; --i) {
                         uA = fma(gA[i], uA, yA[i]);
@@ -618,15 +705,15 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
             // Rotated loop.  Block X: pair 0 backwards (its forward sweeps were done at the end of the previous
             // iteration).  Block Z: the other pair in full, then the NEXT step's scans with pair 0's forward sweeps
             // behind them -- the shuffles' latency hides behind the sweeps of the same basic block.
-            double y0A[8], y0B[8], y30[2] = {0., 0.};
+            F y0A[8], y0B[8], y30[2] = {F(0), F(0)};
             scan();
             fwd_pair(0, y0A, y0B, y30);
             for (int step = 0; step < nsteps; ++step) {
-                if (step < B.opq_lim[0]) back_pair(0, y0A, y0B, y30);  // always true: basic-block boundary
-                if (step < B.opq_lim[1]) {
+                if (RC || step < B.opq_lim[0]) back_pair(0, y0A, y0B, y30);  // always true: basic-block boundary
+                if (RC || step < B.opq_lim[1]) {
 #pragma unroll
                     for (int h = 2; h < NCH; h += 2) {
-                        double yA[8], yB[8], y3[2] = {0., 0.};
+                        F yA[8], yB[8], y3[2] = {F(0), F(0)};
                         fwd_pair(h, yA, yB, y3);
                         back_pair(h, yA, yB, y3);
                     }
@@ -687,7 +774,7 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
                 }
                 __syncwarp();
 #pragma unroll
-                for (int i = 0; i < NODES; ++i) vr[i] = vfin[i * 32 + lane];
+                for (int i = 0; i < NODES; ++i) vr[i] = (F)vfin[i * 32 + lane];
                 __syncwarp();
                 march_levels(std::true_type{});
             }

@@ -140,6 +140,22 @@ __device__ __forceinline__ uint32_t ld16_raw(uint32_t taddr)
         : "memory");
     return r[0] ^ r[5] ^ r[10] ^ r[15];
 }
+// 16 floats = 16 columns in one instruction (two adjacent 8-float blocks)
+__device__ __forceinline__ void ld16(uint32_t taddr, float (&a)[8], float (&b)[8])
+{
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        a[i] = __uint_as_float(r[i]);
+        b[i] = __uint_as_float(r[8 + i]);
+    }
+}
 // the same for eight floats (eight columns)
 __device__ __forceinline__ void ld8(uint32_t taddr, float (&d)[8])
 {
@@ -163,6 +179,16 @@ __device__ __forceinline__ void wait_ld_dep(float (&d)[8])
 {
     asm volatile("tcgen05.wait::ld.sync.aligned;"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]), "+f"(d[4]), "+f"(d[5]), "+f"(d[6]), "+f"(d[7])::"memory");
+}
+__device__ __forceinline__ void wait_ld_dep(float (&a)[8], float (&b)[8])
+{
+    wait_ld_dep(a);
+    asm volatile("" : "+f"(b[0]), "+f"(b[1]), "+f"(b[2]), "+f"(b[3]), "+f"(b[4]), "+f"(b[5]), "+f"(b[6]), "+f"(b[7])::"memory");
+}
+__device__ __forceinline__ void wait_ld_dep(float (&a)[8], float (&b)[8], float (&c)[8])
+{
+    wait_ld_dep(a, b);
+    asm volatile("" : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]), "+f"(c[4]), "+f"(c[5]), "+f"(c[6]), "+f"(c[7])::"memory");
 }
 // Hot-loop variant of the wait.  ptxas tracks the destination registers of a tcgen05.ld (SASS: LDTM) with an
 // ordinary write scoreboard whether or not a tcgen05.wait::ld follows: the first consumer carries the

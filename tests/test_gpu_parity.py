@@ -591,9 +591,12 @@ def test_fp32_march_fixtures(grid):
         assert rel <= 1e-4 and ab <= 5e-5, (name, grid, rel, ab)
 
 
-@pytest.mark.parametrize("x,t,n,variant", [(1024, 200, 1500, 1233), (512, 300, 1500, 1133), (700, 128, 1300, 1233)])
+@pytest.mark.parametrize("x,t,n,variant", [(1024, 200, 1500, 1233), (512, 300, 1500, 1133), (700, 128, 1300, 1233),
+                                              (1024, 200, 1500, 1237), (700, 128, 1300, 1237), (1024, 1024, 1200, 1237), (512, 300, 2500, 1138),
+                                              (300, 128, 2501, 1138), (512, 512, 37, 1138), (256, 256, 5000, 1038), (100, 64, 4999, 1038)])
 def test_fp32_march_layout_w(x, t, n, variant, oracle):
-    """The fp32 march in Layout W (fd1d_warpf.cuh): batches of a device wave or more."""
+    """The fp32 march in Layout W (fd1d_iw.cuh with F = float: 1237 / 1138 / 1038; round 1's fd1d_warpf.cuh: 1233 / 1133 in the
+    experiments build): batches of a device wave or more, short last work units, two / four PDEs per warp."""
     from kwfd1d.synthetic import synthetic_options
 
     o = synthetic_options(n, 2000 + x, european_every=5, call_every=3)

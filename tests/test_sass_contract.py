@@ -34,8 +34,8 @@ def test_every_ldtm_is_scoreboarded_and_waited_for(contract):
     assert problems == [], "\n".join(problems[:20])
     by_name = {name: (n_ldtm, n_sttm, march) for name, _, n_ldtm, n_sttm, march in report}
     # the kernels that keep a~, g~, D, p in tensor memory really do (SASS: LDTM / STTM), and their march loops were found
-    for key, min_loops in (("fd1d_iw_kernelILi4ELi2ELb0ELb0ELi1E", 5), ("fd1d_iw_kernelILi4ELi2ELb1ELb0ELi1E", 10), ("fd1d_iw_kernelILi4ELi2ELb0ELb0ELi2E", 4), ("fd1d_iw_kernelILi4ELi2ELb0ELb0ELi4E", 3), ("fd1d_wide_kernelILi4", 5),
-                           ("fd1d_wide_kernelILi2", 5), ("fd1d_warpf_kernelILi4", 5)):
+    for key, min_loops in (("fd1d_iw_kernelILi4ELi2ELb0ELb0ELi1Ed", 5), ("fd1d_iw_kernelILi4ELi2ELb1ELb0ELi1Ed", 10), ("fd1d_iw_kernelILi4ELi2ELb0ELb0ELi2Ed", 4), ("fd1d_iw_kernelILi4ELi2ELb0ELb0ELi4Ed", 3), ("fd1d_wide_kernelILi4", 5),
+                           ("fd1d_wide_kernelILi2", 5)):
         hits = [v for k, v in by_name.items() if key in k]
         assert hits, key
         for n_ldtm, n_sttm, march in hits:
@@ -43,7 +43,7 @@ def test_every_ldtm_is_scoreboarded_and_waited_for(contract):
             assert len(march) >= min_loops, (key, len(march))
     # the headline kernel: every march loop has 12 LDTM.x32 per step (a~, g~, D, p of a chunk pair + a~, g~ again, two
     # pairs) and at most 16 moves
-    (n_ldtm, n_sttm, march), = [v for k, v in by_name.items() if "fd1d_iw_kernelILi4ELi2ELb0ELb0ELi1E" in k]
+    (n_ldtm, n_sttm, march), = [v for k, v in by_name.items() if "fd1d_iw_kernelILi4ELi2ELb0ELb0ELi1Ed" in k]
     steps = [m for a, b, m in march if m["LDTM"] == 12 and m["DSETP"] == 32]  # the five level-specialised march steps
     assert len(steps) == 5
     for mix in steps:
@@ -57,7 +57,7 @@ def test_the_checker_sees_a_missing_wait(contract):
     import subprocess
 
     sc, report, _ = contract
-    (mangled,) = [name for name, *_ in report if "fd1d_iw_kernelILi4ELi2ELb0ELb0ELi1E" in name]  # the headline kernel
+    (mangled,) = [name for name, *_ in report if "fd1d_iw_kernelILi4ELi2ELb0ELb0ELi1Ed" in name]  # the headline kernel
     sass = subprocess.run(["cuobjdump", "-sass", "-fun", mangled, LIB], capture_output=True, text=True, check=True).stdout
     (name, body), = sc.split_functions(sass).items()
     code = sc.parse_function(body)

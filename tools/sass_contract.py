@@ -220,7 +220,7 @@ def run(lib=DEFAULT_LIB, dump_dir=None, verbose=True):
         n_ldtm, n_sttm, probs, march = check_function(name, code)
         problems += probs
         report.append((name, len(code), n_ldtm, n_sttm, march))
-        if dump_dir and march and "fd1d_iw_kernelILi4ELi2ELb0ELb0ELi1E" in name:
+        if dump_dir and march and "fd1d_iw_kernelILi4ELi2ELb0ELb0ELi1Ed" in name:
             os.makedirs(dump_dir, exist_ok=True)
             a, b, mix = min(march, key=lambda m: abs(m[2]["SHFL"] - 8))  # the two-level loop
             with open(os.path.join(dump_dir, "r2_sass_hotloop_v237_level2.txt"), "w") as f:
