@@ -16,10 +16,12 @@ def run(x,t,n,variant=0,prec="f64",mode="FD1D-GPU",**kw):
     o=synthetic_options(n,5,european_every=4,call_every=3); o=np.concatenate([o,o[:n//5]])
     err,got=p.price(o); assert err=="",err
     print("ok",mode,x,t,n,p.info()["variant"],float(got.sum()))
-run(1024,12,44,237); run(700,12,41,237); run(1024,12,24,201); run(512,12,40,133); run(300,12,40,133); run(512,12,24,101)
-run(256,12,40,1); run(2048,10,24,336); run(1100,10,9,336); run(4096,8,12,436); run(3000,8,5,436); run(2048,8,6,301); run(4096,8,4,401)
-run(1024,12,40,1233,"f32"); run(512,12,40,1101,"f32"); run(1024,12,24,1201,"f32")
-run(1024,12,42,0,mode="FD1D-BS-GPU",**{"FD1D.GPU.BS_FUSED":4}); run(512,12,42,0,mode="FD1D-BS-GPU",**{"FD1D.GPU.BS_FUSED":4})
+run(1024,12,44,237); run(700,12,41,237); run(1024,12,24,201); run(512,12,41,138); run(300,12,43,138); run(512,12,24,101)
+run(256,12,41,38); run(70,12,43,38); run(256,12,40,1); run(2048,10,24,336); run(1100,10,9,336); run(4096,8,12,436); run(3000,8,5,436); run(2048,8,6,301); run(4096,8,4,401)
+run(1024,12,41,1237,"f32"); run(512,12,41,1138,"f32"); run(256,12,43,1038,"f32"); run(512,12,40,1101,"f32"); run(1024,12,24,1201,"f32")
+run(1024,12,42,0,mode="FD1D-BS-GPU",**{"FD1D.GPU.BS_FUSED":4}); run(512,12,43,0,mode="FD1D-BS-GPU",**{"FD1D.GPU.BS_FUSED":4})
+run(256,12,41,0,mode="FD1D-BS-GPU",**{"FD1D.GPU.BS_FUSED":4}); run(2048,8,9,0,mode="FD1D-BS-GPU",**{"FD1D.GPU.BS_FUSED":4})
+run(512,10,1100,0)  # device-side compression, both batch-size classes launched (class split)
 run(1024,12,42,0,mode="FD1D-BS-GPU",**{"FD1D.GPU.BS_FUSED":1}); run(1024,8,40,0,**{"FD1D.GPU.LAYOUT":"soa"})
 run(1024,12,44,0,**{"FD1D.GPU.DEVICES":"0,0"})
 PY
