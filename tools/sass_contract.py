@@ -13,7 +13,7 @@ instruction, over every control-flow path that leaves an LDTM:
   2. on every path from an LDTM, an instruction whose wait mask (bits 116-121) contains that scoreboard comes
      before, or is, the first instruction that touches a destination register of the load;
   3. the march loops (backward-branch bodies with LDTM and >= 100 DFMA / FFMA) of the dispatched kernels contain no
-     local-memory store and at most two loads (LDL / STL: spills) -- a spilled march state is a silent 30 %
+     local-memory store and at most four loads (LDL / STL: spills) -- a spilled march state is a silent 30 %
      regression (measured: 24 STL + 24 LDL per step took the headline kernel from 23.9 to 40.4 ms);
   4. the kernels that are supposed to keep their coefficients in tensor memory do contain LDTM and STTM.
 
@@ -197,10 +197,11 @@ def check_function(name, code):
             if spills:
                 msg = "%s: march loop @%x..%x has %d local-memory accesses (spills)" % (name, code[a].addr, code[b].addr,
                                                                                         len(spills))
-                # a lone LDL of a loop-invariant value is tolerated (the rare five-level loop of the fused FD1D-BS
-                # kernel re-reads one); a store, or more than two accesses, is a real spill of the march's state
+                # a few LDLs of loop-invariant values are tolerated (the rare four- and five-level loops of the fused
+                # FD1D-BS kernel re-read two / four scan multipliers); a store, or more than four loads, is a real spill
+                # of the march's state
                 stores = [i for i in spills if i.base == "STL"]
-                if any(k in name for k in NO_SPILL_KERNELS) and (stores or len(spills) > 2):
+                if any(k in name for k in NO_SPILL_KERNELS) and (stores or len(spills) > 4):
                     problems.append(msg)
                 else:
                     warnings.append(msg)
