@@ -1,5 +1,5 @@
 # CPU model: how many polishing sweeps until bitwise convergence, for typical and stiff PDEs
-import sys; sys.path.insert(0,'/root/repo/oracle'); sys.path.insert(0,'/root/repo/kwinto-cuda_b200'); sys.path.insert(0,'/root/repo/tests')
+import sys; import os; R=os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path[:0]=[R+'/oracle', R+'/kwinto-cuda_b200', R+'/tests']
 import numpy as np, pyoracle, scheme_model
 from kwfd1d.synthetic import synthetic_options
 o = pyoracle.Oracle()
