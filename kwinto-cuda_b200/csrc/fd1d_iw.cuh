@@ -31,8 +31,9 @@ __device__ __noinline__ double payoff_node_ni(bool put, double x) { return payof
 template <int NCH>
 struct IwSmem {
     static constexpr int N = 8 * NCH * 32;  // nodes per PDE tile
-    static constexpr int SCR = 40 * 32;     // scratch per warp [row][lane]: half-chunk constants [5 * 4], carried half-chunk
-                                            // values e_3, l_4 [2 * 4], chunk scalars of the set-up [12]
+    static constexpr int SCR = 44 * 32;     // scratch per warp [row][lane]: half-chunk constants [5 * 4], carried half-chunk
+                                            // values e_3, l_4 [2 * 4], chunk scalars of the set-up [12]; during the set-up the
+                                            // pivots beta of the lane's 32 nodes (rows 0-27 and 40-43)
     // doubles per warp: final v of its PDE [N] (the payoff stage during set-up) | set-up scratch [SCR]
     static constexpr size_t bytes() { return sizeof(double) * (size_t)(4 * (N + SCR)); }
 };
@@ -128,12 +129,15 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
             double* s_v = vfin;            // [NODES][32] payoff, until the registers take it
             double* s_k = scr + 28 * 32;   // [3 * NCH][32] chunk scalars
             double* s_h = scr;             // [5 * NCH][32] half-chunk constants P_lo, P_hi, Q_lo, Q_hi, R_hi (D4)
+            double* s_b = scr;             // [NODES][32] the pivots beta, until 1/beta is in tensor memory (rows 0-27, 40-43)
+            auto beta_row = [](int n) { return n < 28 ? n : n + 12; };
             // ---- grid, payoff, projection floor, rows of B (parked in tensor memory)
             double bu_carry = 0.;
             {
                 double x_m1 = pl ? x_node_ni(sc, B.density, j0 - 1) : 0.;
                 double x_0 = x_node_ni(sc, B.density, j0);
                 if (pl == 0) x_m1 = x_0;
+                double inv_d = pl ? 1. / (x_0 - x_m1) : 0.;  // 1 / (x_j - x_{j-1}), handed from row to row (b_row_chained)
 #pragma unroll 1
                 for (int c = 0; c < NCH; ++c) {
                     double xl[10];  // nodes 8c - 1 .. 8c + 8 of this lane
@@ -152,7 +156,7 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
                         s_v[(8 * c + i) * 32 + lane] = p;
                         // projection skips the last node (src/Math/kwFd1d.cpp:130); European: never
                         t8[i] = (sc.american && j < xDim - 1) ? (F)p : (F)-CUDART_INF;
-                        b_row(sc, j, xDim, xl[i], xl[1 + i], xl[2 + i], bl[i], bb[i], bu[i]);
+                        b_row_chained(sc, j, xDim, xl[i], xl[1 + i], xl[2 + i], inv_d, inv_d, bl[i], bb[i], bu[i]);
                     }
                     tmem::st8(tbase + T_P + CW * c, t8);
                     tmem::st8(tbase + T_A + 16 * c, bl);
@@ -227,8 +231,10 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
                         tmem::wait_ld_dep(bl, bb, bu);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
+                            // the reference's order (src/Math/kwMath.cpp:32-33): gam = au[j-1] / bet;  bet = a[j] - al[j] * gam
                             const double gam = (i ? bu[i > 0 ? i - 1 : 0] : bu_carry) / prev;
                             prev = __dsub_rn(bb[i], __dmul_rn(bl[i], gam));
+                            s_b[beta_row(8 * c + i) * 32 + lane] = prev;  // kept: the last sweep's pivots ARE the pivots
                         }
                         bu_carry = bu[7];
                     }
@@ -238,26 +244,18 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
                     pin = pnew;
                     if (!__any_sync(FULL, changed)) break;
                 }
-                // ---- pivots inside every chunk, in the reference's order (src/Math/kwMath.cpp:32-33):
-                //      gam = au[j-1] / bet;  bet = a[j] - al[j] * gam;  1/beta replaces the diagonal in tensor memory
-                bu_carry = bu_prev_lane;
-                double prev = pin;
+                // ---- The sweep that found no incoming pivot changed ran the reference's recurrence from the final incoming pivots:
+                //      its beta are the pivots.  1/beta replaces the diagonal in tensor memory (independent divisions, no chain);
+                //      max |beta| scales the scan-truncation tolerance.
 #pragma unroll 1
                 for (int c = 0; c < NCH; ++c) {
-                    double bl[8], bb[8], bu[8];
-                    tmem::ld8(tbase + T_A + 16 * c, bl);
-                    tmem::ld8(tbase + T_G + 16 * c, bb);
-                    tmem::ld8(tbase + T_D + 16 * c, bu);
-                    tmem::wait_ld_dep(bl, bb, bu);
                     double ib[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const double gam = (i ? bu[i > 0 ? i - 1 : 0] : bu_carry) / prev;
-                        const double beta = __dsub_rn(bb[i], __dmul_rn(bl[i], gam));
+                        const double beta = s_b[beta_row(8 * c + i) * 32 + lane];
                         ib[i] = 1. / beta;
-                        prev = beta;
+                        bmax = fmax(bmax, fabs(beta));
                     }
-                    bu_carry = bu[7];
                     tmem::st8(tbase + T_G + 16 * c, ib);
                 }
                 tmem::wait_st();
@@ -339,8 +337,6 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
                         s_h[(5 * c + 3) * 32 + lane] = ((g[7] * g[6]) * g[5]) * g[4];  // Q_hi
                         s_h[(5 * c + 4) * 32 + lane] = Rh;
                     }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) bmax = fmax(bmax, D[i] != 0. ? fabs(2. / D[i]) : 1.);
                     ib_prev = ib[7];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) ib[i] = ibn[i];
