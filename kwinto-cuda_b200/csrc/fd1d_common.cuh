@@ -231,4 +231,39 @@ __device__ __forceinline__ void price_option(const Fd1dBatch& B, uint32_t oi, XS
     B.prices[oi] = __dmul_rn(o.k, num / (x1 - x0));
 }
 
+// The same for a caller that does not keep the grid (fd1d_iw.cuh recomputes x_j = density sinh(...), ~100 instructions a node):
+// the position of x_ on the sinh grid is known analytically, so the lower bound is found by stepping from ceil of the fractional
+// index until x[lo-1] < x_ <= x[lo] holds for the COMPUTED nodes -- the answer of the reference's search, with 2-3 grid evaluations
+// instead of log2(xDim) + 2.
+template <class VS>
+__device__ __forceinline__ void price_option_sinh_grid(const Fd1dBatch& B, const PdeScalars& sc, uint32_t oi, VS vs)
+{
+    const kw_option o = load_option(B.opts + oi);
+    const double xq = log(o.s / o.k);
+    const int xDim = B.xDim;
+    const double t = (asinh(xq / B.density) - sc.yMin) / (sc.yMax - sc.yMin) * (double)(xDim - 1);
+    int lo = !(t > 0.) ? 0 : (t >= (double)xDim ? xDim : (int)ceil(t));  // (NaN: 0, as the search below then answers)
+    double x_hi = lo < xDim ? x_node(sc, B.density, lo) : CUDART_INF;      // x[lo]
+    double x_lw = lo > 0 ? x_node(sc, B.density, lo - 1) : -CUDART_INF;    // x[lo - 1]
+    while (lo > 0 && !(x_lw < xq)) {
+        --lo;
+        x_hi = x_lw;
+        x_lw = lo > 0 ? x_node(sc, B.density, lo - 1) : -CUDART_INF;
+    }
+    while (lo < xDim && x_hi < xq) {
+        ++lo;
+        x_lw = x_hi;
+        x_hi = lo < xDim ? x_node(sc, B.density, lo) : CUDART_INF;
+    }
+    if (lo == 0 || lo == xDim) {
+        B.prices[oi] = CUDART_NAN;
+        atomicAdd(&B.status[0], 1u);
+        atomicMin(&B.status[1], oi);
+        return;
+    }
+    const double x1 = x_hi, x0 = x_lw;
+    const double num = __dadd_rn(__dmul_rn(x1 - xq, vs(lo - 1)), __dmul_rn(xq - x0, vs(lo)));
+    B.prices[oi] = __dmul_rn(o.k, num / (x1 - x0));
+}
+
 }  // namespace kwfd1d

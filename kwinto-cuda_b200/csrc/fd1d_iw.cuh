@@ -229,6 +229,7 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
                         tmem::ld8(tbase + T_G + 16 * c, bb);
                         tmem::ld8(tbase + T_D + 16 * c, bu);
                         tmem::wait_ld_dep(bl, bb, bu);
+                        const double was = s_b[beta_row(8 * c + 7) * 32 + lane];  // the previous sweep's pivot at the chunk's end
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             // the reference's order (src/Math/kwMath.cpp:32-33): gam = au[j-1] / bet;  bet = a[j] - al[j] * gam
@@ -237,6 +238,14 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
                             s_b[beta_row(8 * c + i) * 32 + lane] = prev;  // kept: the last sweep's pivots ARE the pivots
                         }
                         bu_carry = bu[7];
+                        // From a chunk end where every lane reproduces the previous sweep's pivot bit for bit, the rest of the
+                        // sweep would reproduce the rest of the previous one (same recurrence, same input): skip it.  The
+                        // corrections of a sweep die out within a few nodes, so every sweep but the first stops after one chunk.
+                        if (sweep > 0 && c < NCH - 1 &&
+                            __all_sync(FULL, __double_as_longlong(prev) == __double_as_longlong(was))) {
+                            prev = s_b[beta_row(NODES - 1) * 32 + lane];
+                            break;
+                        }
                     }
                     double pnew = __shfl_up_sync(FULL, prev, 1, LPP);
                     if (pl == 0) pnew = CUDART_INF;
@@ -745,7 +754,7 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
             const double* vmine = vfin + ph * XT;
             for (uint32_t q = q0 + pl; q < q1; q += LPP) {
                 const uint32_t oi = B.csr_opt ? __ldg(B.csr_opt + q) : q;
-                price_option(Bo, oi, [&](int j) { return x_node(sc, B.density, j); }, [&](int j) { return vmine[j]; });
+                price_option_sinh_grid(Bo, sc, oi, [&](int j) { return vmine[j]; });
             }
             __syncwarp();  // vfin is rewritten by the next emit
         };
