@@ -210,12 +210,13 @@ __device__ __forceinline__ void setup_lu(const Fd1dBatch& B, const PdeScalars& s
         double bl[M], bb[M], bu[M];
         const double x_before = xs[k > 0 ? k * M - 1 : 0];
         const double x_after = xs[k < P - 1 ? k * M + M : N - 1];
+        double inv_d = k > 0 ? 1. / (xl[0] - x_before) : 0.;  // 1 / (x_j - x_{j-1}), handed from row to row (b_row_chained)
 #pragma unroll
         for (int i = 0; i < M; ++i) {
             const int j = k * M + i;
             const double xm = i ? xl[i - 1] : x_before;           // = xs[j > 0 ? j - 1 : 0]
             const double xp = i < M - 1 ? xl[i + 1] : x_after;    // = xs[j < N - 1 ? j + 1 : N - 1]
-            b_row(sc, j, xDim, xm, xl[i], xp, bl[i], bb[i], bu[i]);
+            b_row_chained(sc, j, xDim, xm, xl[i], xp, inv_d, inv_d, bl[i], bb[i], bu[i]);
         }
         s_bu_last[k] = bu[M - 1];
         __syncthreads();
@@ -283,6 +284,7 @@ __device__ __forceinline__ void setup_lu(const Fd1dBatch& B, const PdeScalars& s
         // incoming pivot and hands the result to the next chunk, until no incoming pivot changes any more (chunk k is exact
         // after k sweeps at the latest; with the contraction a few sweeps do, ~25 on the stiffest grids).  The fixed point IS
         // the serial recurrence of src/Math/kwMath.cpp:30-38, bit for bit.
+        double beta[M];  // the last sweep's pivots ARE the pivots (it ran from the final incoming pivot)
         {
             double pin = s_bin[k];
             __syncthreads();  // every thread holds its first guess before a neighbour overwrites it
@@ -291,8 +293,10 @@ __device__ __forceinline__ void setup_lu(const Fd1dBatch& B, const PdeScalars& s
                 double prev = pin;
 #pragma unroll
                 for (int i = 0; i < M; ++i) {
+                    // the reference's order (src/Math/kwMath.cpp:32-33): gam = au[j-1] / bet;  bet = a[j] - al[j] * gam
                     const double gam = (i ? bu[i - 1] : bu_prev) / prev;
                     prev = __dsub_rn(bb[i], __dmul_rn(bl[i], gam));
+                    beta[i] = prev;
                 }
                 if (k < P - 1) s_bin[k + 1] = prev;
                 __syncthreads();
@@ -303,19 +307,9 @@ __device__ __forceinline__ void setup_lu(const Fd1dBatch& B, const PdeScalars& s
             }
         }
 
-        // pivots inside the chunk, in the reference's order (src/Math/kwMath.cpp:32-33):
-        // gam = au[j-1] / bet;  bet = a[j] - al[j] * gam
         double ib[M];
-        {
-            double prev = s_bin[k];
 #pragma unroll
-            for (int i = 0; i < M; ++i) {
-                const double gam = (i ? bu[i - 1] : bu_prev) / prev;
-                const double beta = __dsub_rn(bb[i], __dmul_rn(bl[i], gam));
-                ib[i] = 1. / beta;
-                prev = beta;
-            }
-        }
+        for (int i = 0; i < M; ++i) ib[i] = 1. / beta[i];
         s_ib_first[k] = ib[0];
         s_ib_last[k] = ib[M - 1];
         __syncthreads();
