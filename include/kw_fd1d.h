@@ -117,6 +117,9 @@ typedef struct kw_fd1d_info {
     int32_t n_devices;        /* devices the handle owns (1 for a single-device handle)      */
     int32_t devices_used;     /* devices the last price call spread the batch over            */
     double last_wall_ms;      /* multi-device: host wall time of the last price call (last_kernel_ms = max over devices) */
+    uint32_t long_chains;     /* chains of the last SYNCHRONISED call whose options (> 512) were priced by the CTA-per-chain
+                                 value kernel instead of the marching warp (fused FD1D-BS counts both solutions) */
+    uint32_t reserved_;
 } kw_fd1d_info;
 
 void kw_fd1d_config_default(kw_fd1d_config* cfg);

@@ -256,6 +256,7 @@ __global__ void status_reset_kernel(unsigned int* status, int keep_errors)
         status[2] = status[3] = status[4] = status[5] = status[6] = status[7] = 0u;
     }
     status[8] = 0u;  // work counter of the independent-warp kernels
+    status[9] = 0u;  // long-chain slots handed out
 }
 
 // device-side chain compression of `n` device-resident options; fills the batch's PDE tables
@@ -378,6 +379,7 @@ struct kw_fd1d_handle {
     int launches = 0;  // kernels launched by the current / last price call
     uint64_t last_n_pde = 0;
     unsigned int mode_count[6] = {0, 0, 0, 0, 0, 0};
+    unsigned int long_chains = 0;           // slots fd1d_long_value_kernel priced in the last synchronised call
 
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -390,6 +392,8 @@ struct kw_fd1d_handle {
     DevBuf<uint32_t> d_chain;  // device-side compression: one slab carved into the ChainTable arrays
     bool dev_compressed = false;
     DevBuf<unsigned int> d_status;
+    DevBuf<double> d_long;        // final v of the chains with more than KW_LONG_CHAIN options (fd1d_long_value_kernel)
+    DevBuf<uint32_t> d_long_meta;
     DevBuf<double> d_soa;
     PinBuf<uint32_t> h_idx;  // rep | start | csr staging
     PinBuf<unsigned int> h_status;
@@ -483,6 +487,19 @@ int launch_batch(kw_fd1d_handle* h, Fd1dBatch B, cudaStream_t st)
             h->launches += 1;
             return cudaSuccess;
         };
+        // long chains of the independent-warp kernels: slots for the final v, priced by a kernel of their own afterwards
+        const RegVariant* vbig = fused ? h->var_bs : h->var;
+        const bool iw = vbig->fn && vbig->pdes_per_cta >= 4 && vbig->tmem_cols == 256 && B.csr_start && B.n_opt > KW_LONG_CHAIN &&
+                        !getenv("KW_FD1D_NO_LONG");  // (the variable exists for tools/long_chain_probe.py's comparison)
+        const int tile = vbig->M * vbig->P;
+        if (iw) {
+            B.long_cap = (B.n_opt / KW_LONG_CHAIN + 1) * (fused ? 2u : 1u);
+            KW_CUDA(h, h->d_long.reserve((size_t)B.long_cap * tile));
+            KW_CUDA(h, h->d_long_meta.reserve(B.long_cap));
+            B.long_ws = h->d_long.p;
+            B.long_meta = h->d_long_meta.p;
+            B.long_count = B.status + 9;
+        }
         KW_CUDA(h, cudaEventRecord(h->ev0, st));
         h->class_split = 0;
         if (!fused && h->var_small && B.n_pde_dev && B.n_pde >= h->small_below) {
@@ -503,6 +520,10 @@ int launch_batch(kw_fd1d_handle* h, Fd1dBatch B, cudaStream_t st)
             const RegVariant* v = fused ? h->var_bs : (small ? h->var_small : h->var);
             h->last_var = v;
             KW_CUDA(h, run(v, fused ? h->ctas_per_sm_bs : (small ? h->ctas_per_sm_small : h->ctas_per_sm), B, B.n_pde));
+        }
+        if (iw) {
+            fd1d_long_value_kernel<<<(int)std::min<uint32_t>(B.long_cap, (uint32_t)(4 * h->sm_count)), 256, 0, st>>>(B, tile);
+            h->launches += 1;
         }
         KW_CUDA(h, cudaEventRecord(h->ev1, st));
         h->ev_valid = true;
@@ -659,6 +680,7 @@ int price_resident(kw_fd1d_handle* h, const kw_option* assets, size_t n, const k
     B.opts = d_opts_p;
     B.prices = d_out;
     B.prices_eu = d_out_eu;  // non-null: the fused FD1D-BS march (both solutions of every chain)
+    B.n_opt = (uint32_t)n;
     B.status = h->d_status.p;
     B.tDim = (int32_t)h->cfg.t_grid_size;
     B.xDim = (int32_t)h->cfg.x_grid_size;
@@ -697,11 +719,12 @@ int price_resident(kw_fd1d_handle* h, const kw_option* assets, size_t n, const k
 
 int check_status(kw_fd1d_handle* h, cudaStream_t st, const kw_option* host_assets)
 {
-    KW_CUDA(h, h->h_status.reserve(8));
-    KW_CUDA(h, cudaMemcpyAsync(h->h_status.p, h->d_status.p, 8 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    KW_CUDA(h, h->h_status.reserve(16));
+    KW_CUDA(h, cudaMemcpyAsync(h->h_status.p, h->d_status.p, 10 * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
     KW_CUDA(h, cudaStreamSynchronize(st));
     h->unsynced = false;
     for (int i = 0; i < 6; ++i) h->mode_count[i] = h->h_status.p[2 + i];
+    h->long_chains = h->h_status.p[9];
     if (h->dev_compressed) {
         // the PDE count stayed on the device; it is the sum of the per-mode counters of the march
         uint64_t m = 0;
@@ -947,6 +970,8 @@ void kw_fd1d_destroy(kw_fd1d_handle* h)
     h->d_start.release();
     h->d_csr.release();
     h->d_chain.release();
+    h->d_long.release();
+    h->d_long_meta.release();
     h->d_ws.release();
     h->d_status.release();
     h->d_soa.release();
@@ -1092,6 +1117,7 @@ int kw_fd1d_price_device(kw_fd1d_handle* h, const kw_option* d_assets, size_t n,
     B.opts = d_assets;
     B.prices = d_prices;
     B.status = h->d_status.p;
+    B.n_opt = (uint32_t)n;
     B.n_pde = (uint32_t)n;
     B.tDim = (int32_t)h->cfg.t_grid_size;
     B.xDim = (int32_t)h->cfg.x_grid_size;
@@ -1158,6 +1184,7 @@ int kw_fd1d_get_info(const kw_fd1d_handle* hc, kw_fd1d_info* info)
         info->n_devices = (int32_t)h->shards.size();
         info->devices_used = (int32_t)used;
         info->last_wall_ms = h->last_wall_ms;
+        for (uint32_t g = 1; g < used; ++g) info->long_chains += h->shards[g]->long_chains;
         return KW_FD1D_OK;
     }
     memset(info, 0, sizeof *info);
@@ -1181,6 +1208,7 @@ int kw_fd1d_get_info(const kw_fd1d_handle* hc, kw_fd1d_info* info)
     info->launches = h->launches;
     info->last_n_pde = h->last_n_pde;
     for (int i = 0; i < 6; ++i) info->mode_count[i] = h->mode_count[i];
+    info->long_chains = h->long_chains;
     info->last_kernel_ms = 0.;
     if (h->ev_valid && cudaEventSynchronize(h->ev1) == cudaSuccess) {
         float ms = 0.f;

@@ -52,7 +52,15 @@ struct Fd1dBatch {
     // PDE-count class of this launch: with the count known only on the device (n_pde_dev), capi.cu launches the kernel of
     // every class and the ones whose class [pde_lo, pde_hi) does not hold the count see an empty batch
     uint32_t pde_lo, pde_hi;
+    // Long chains (fd1d_iw.cuh): a warp that finds more than KW_LONG_CHAIN options on its PDE does not interpolate them itself;
+    // it leaves the final v in a workspace slot and fd1d_long_value_kernel prices them with a CTA per chain afterwards.
+    double* long_ws;         // [long_cap][nodes per PDE tile], or null (feature off: no chain compression)
+    uint32_t* long_meta;     // [long_cap] PDE id | (European copy of the fused FD1D-BS march) << 31
+    unsigned int* long_count;  // slots handed out (status[9], zeroed before every launch)
+    uint32_t long_cap;
+    uint32_t n_opt;          // options in the batch
 };
+#define KW_LONG_CHAIN 512u
 
 __device__ __forceinline__ uint32_t batch_n_pde(const Fd1dBatch& B)
 {
@@ -264,6 +272,30 @@ __device__ __forceinline__ void price_option_sinh_grid(const Fd1dBatch& B, const
     const double x1 = x_hi, x0 = x_lw;
     const double num = __dadd_rn(__dmul_rn(x1 - xq, vs(lo - 1)), __dmul_rn(xq - x0, vs(lo)));
     B.prices[oi] = __dmul_rn(o.k, num / (x1 - x0));
+}
+
+// The options of the chains that fd1d_iw_kernel deferred (Fd1dBatch::long_ws): a thread per option, gridDim / chains CTAs per chain.
+__global__ void __launch_bounds__(256) fd1d_long_value_kernel(const Fd1dBatch B, int XT)
+{
+    const uint32_t cnt = min(*B.long_count, B.long_cap);
+    if (cnt == 0) return;
+    const uint32_t seg_n = max(1u, gridDim.x / cnt);  // CTAs per chain: few long chains spread over the whole grid
+    for (uint32_t b = blockIdx.x; b < cnt * seg_n; b += gridDim.x) {
+        const uint32_t s = b % cnt, seg = b / cnt;
+        const uint32_t meta = B.long_meta[s];
+        const uint32_t pde = meta & 0x7fffffffu;
+        const uint32_t rep = B.pde_rep ? __ldg(B.pde_rep + pde) : pde;
+        const PdeScalars sc = pde_scalars(load_option(B.opts + rep), B);
+        Fd1dBatch Bo = B;
+        if (meta >> 31) Bo.prices = B.prices_eu;
+        uint32_t q0, q1;
+        chain_range(B, pde, q0, q1);
+        const double* v = B.long_ws + (size_t)s * XT;
+        for (uint32_t q = q0 + seg * blockDim.x + threadIdx.x; q < q1; q += seg_n * blockDim.x) {
+            const uint32_t oi = B.csr_opt ? __ldg(B.csr_opt + q) : q;
+            price_option_sinh_grid(Bo, sc, oi, [&](int j) { return __ldg(v + j); });
+        }
+    }
 }
 
 }  // namespace kwfd1d

@@ -742,7 +742,7 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
             }
         };
         // ================= epilogue: interpolate every option of this chain ===============================
-        auto emit = [&](double* out) {
+        auto emit = [&](double* out, bool eu) {
 #pragma unroll
             for (int i = 0; i < NODES; ++i) vfin[lane * NODES + i] = vr[i];
             __syncwarp();
@@ -752,6 +752,17 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
             chain_range(B, my_pde, q0, q1);
             if (!live) q1 = q0;
             const double* vmine = vfin + ph * XT;
+            // a long chain is handed to fd1d_long_value_kernel (a CTA per chain) instead of LPP lanes of this warp
+            const bool want = B.long_ws && q1 - q0 > KW_LONG_CHAIN && my_pde < 0x80000000u;
+            uint32_t slot = 0;
+            if (want && pl == 0) slot = atomicAdd(B.long_count, 1u);
+            slot = __shfl_sync(FULL, slot, 0, LPP);
+            if (want && slot < B.long_cap) {
+                double* w = B.long_ws + (size_t)slot * XT;
+                for (int j = pl; j < XT; j += LPP) w[j] = vmine[j];
+                if (pl == 0) B.long_meta[slot] = my_pde | (eu ? 0x80000000u : 0u);
+                q1 = q0;
+            }
             for (uint32_t q = q0 + pl; q < q1; q += LPP) {
                 const uint32_t oi = B.csr_opt ? __ldg(B.csr_opt + q) : q;
                 price_option_sinh_grid(Bo, sc, oi, [&](int j) { return vmine[j]; });
@@ -764,7 +775,7 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
             const int bucket = B.max_mode == 0 ? 0 : (own == MAXLEV ? 1 : 6 - own);
             atomicAdd(&B.status[2 + bucket], 1u);
         }
-        emit(B.prices);
+        emit(B.prices, false);
         if constexpr (BS) {
             if (__any_sync(FULL, sc.american)) {  // (PACK > 1: a PDE given as European marches to the same values again)
                 // the European copy: payoff again (src/Pricer/kwFd1d.cpp:127-139, as in the set-up), same LU (still in
@@ -783,7 +794,7 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
                 __syncwarp();
                 march_levels(std::true_type{});
             }
-            emit(B.prices_eu);  // a chain given as European: one march, both arrays
+            emit(B.prices_eu, true);  // a chain given as European: one march, both arrays
         }
         __syncwarp();  // vfin is rewritten by the next PDE
     }

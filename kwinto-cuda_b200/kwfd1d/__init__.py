@@ -44,7 +44,8 @@ class _CInfo(C.Structure):  # struct kw_fd1d_info
                 ("regs_per_thread", C.c_int32), ("smem_per_cta", C.c_int32), ("grid", C.c_int32),
                 ("sm_clock_khz", C.c_int32), ("launches", C.c_int32), ("last_kernel_ms", C.c_double),
                 ("last_n_pde", C.c_uint64), ("mode_count", C.c_uint32 * 6), ("device_name", C.c_char * 128),
-                ("n_devices", C.c_int32), ("devices_used", C.c_int32), ("last_wall_ms", C.c_double)]
+                ("n_devices", C.c_int32), ("devices_used", C.c_int32), ("last_wall_ms", C.c_double),
+                ("long_chains", C.c_uint32), ("reserved_", C.c_uint32)]
 
 
 _lib = None

@@ -333,6 +333,46 @@ def test_dispatch_goes_by_chains_not_options():
         assert err == "" and np.array_equal(d, e)
 
 
+@pytest.mark.parametrize("x,t,variant,mode", [(1024, 48, 237, "FD1D-GPU"), (512, 48, 138, "FD1D-GPU"), (256, 48, 38, "FD1D-GPU"),
+                                                (1024, 48, 257, "FD1D-BS-GPU"), (512, 48, 158, "FD1D-BS-GPU"), (700, 48, 1237, "FD1D-GPU")])
+def test_long_chains_are_priced_by_their_own_kernel(x, t, variant, mode):
+    """Few chains with thousands of options next to many short ones: the independent-warp kernels hand every chain of more than
+    512 options to fd1d_long_value_kernel (a CTA per chain) instead of interpolating it with one warp's lanes.  Same prices, bit
+    for bit, as the uncompressed batch (one PDE per option, no chains at all), including an out-of-range option inside a long chain."""
+    from kwfd1d.synthetic import synthetic_options
+
+    rng = np.random.default_rng(x + t)
+    base = synthetic_options(1200, 17, european_every=4, call_every=3)
+    long_idx = [3, 250, 251, 900]  # 251: neighbour of 250 in a packed warp; mixed exercise / parity
+    extra = []
+    for i, n_members in zip(long_idx, (5000, 700, 513, 2000)):
+        e = np.repeat(base[i:i + 1], n_members)
+        e["k"] = base[i]["k"] * rng.uniform(0.7, 1.4, size=n_members)
+        e["s"] = base[i]["s"] * rng.uniform(0.9, 1.1, size=n_members)
+        extra.append(e)
+    o = np.concatenate([base] + extra)
+    o = o[rng.permutation(o.shape[0])]
+    kw = {"FD1D.GPU.PRECISION": "f32"} if variant >= 1000 else {}
+    if mode == "FD1D-BS-GPU":
+        kw["FD1D.GPU.BS_FUSED"] = 4
+    else:
+        kw["FD1D.GPU.VARIANT"] = variant
+    a = make_pricer(t, x, mode=mode, **kw)
+    err, pa = a.price(o)
+    assert err == "" and a.info()["variant"] == variant and a.info()["last_n_pde"] == 1200, a.info()
+    assert a.info()["long_chains"] == (8 if mode == "FD1D-BS-GPU" else 4), a.info()  # fused FD1D-BS: both solutions of a chain
+    b = make_pricer(t, x, mode=mode, **dict(kw, **{"FD1D.GPU.COMPRESS": 0}))
+    err, pb = b.price(o)
+    assert err == "" and b.info()["last_n_pde"] == o.shape[0] and b.info()["long_chains"] == 0
+    assert np.array_equal(pa, pb), float(np.max(np.abs(pa - pb)))
+    bad = o.copy()
+    j = int(np.nonzero((o["t"] == base[3]["t"]) & (o["z"] == base[3]["z"]))[0][7])
+    bad["s"][j] = 1e300
+    err, pc = a.price(bad)
+    keep = np.arange(o.shape[0]) != j
+    assert "not in range" in err and np.isnan(pc[j]) and np.array_equal(pc[keep], pa[keep])
+
+
 def test_compression_and_permutation_are_bit_neutral():
     g = load_golden("portfolio_fd1d")
     o = g["options"]
