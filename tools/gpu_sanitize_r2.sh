@@ -22,6 +22,14 @@ run(1024,12,41,1237,"f32"); run(512,12,41,1138,"f32"); run(256,12,43,1038,"f32")
 run(1024,12,42,0,mode="FD1D-BS-GPU",**{"FD1D.GPU.BS_FUSED":4}); run(512,12,43,0,mode="FD1D-BS-GPU",**{"FD1D.GPU.BS_FUSED":4})
 run(256,12,41,0,mode="FD1D-BS-GPU",**{"FD1D.GPU.BS_FUSED":4}); run(2048,8,9,0,mode="FD1D-BS-GPU",**{"FD1D.GPU.BS_FUSED":4})
 run(512,10,1100,0)  # device-side compression, both batch-size classes launched (class split)
+def long_chain(x,t,mode="FD1D-GPU",**kw):
+    cfg=kwfd1d.Config(PRICER=mode); cfg.set("FD1D.T_GRID_SIZE",t); cfg.set("FD1D.X_GRID_SIZE",x)
+    for k,v in kw.items(): cfg.set(k,v)
+    err,p=kwfd1d.PricerFactory.create(cfg); assert err=="",err
+    o=synthetic_options(1000,6,european_every=4,call_every=3); e=np.repeat(o[5:6],700); e["k"]*=np.linspace(0.8,1.2,700); o=np.concatenate([o,e])
+    err,got=p.price(o); assert err=="",err
+    print("ok long chain",mode,x,t,p.info()["variant"],p.info()["long_chains"],float(got.sum()))
+long_chain(1024,8); long_chain(512,8); long_chain(256,8); long_chain(1024,8,"FD1D-BS-GPU",**{"FD1D.GPU.BS_FUSED":4})
 run(1024,12,42,0,mode="FD1D-BS-GPU",**{"FD1D.GPU.BS_FUSED":1}); run(1024,8,40,0,**{"FD1D.GPU.LAYOUT":"soa"})
 run(1024,12,44,0,**{"FD1D.GPU.DEVICES":"0,0"})
 PY
