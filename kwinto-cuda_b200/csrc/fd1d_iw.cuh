@@ -778,14 +778,23 @@ __global__ void __launch_bounds__(128, MINB) fd1d_iw_kernel(const Fd1dBatch B)
         emit(B.prices, false);
         if constexpr (BS) {
             if (__any_sync(FULL, sc.american)) {  // (PACK > 1: a PDE given as European marches to the same values again)
-                // the European copy: payoff again (src/Pricer/kwFd1d.cpp:127-139, as in the set-up), same LU (still in
-                // tensor memory), no projection
+                // the European copy: payoff again (src/Pricer/kwFd1d.cpp:127-139), same LU (still in tensor memory), no
+                // projection.  An American chain's projection floor IS its payoff on the nodes 0 .. xDim-2 and still sits in
+                // tensor memory: only the last node's payoff is evaluated again (and, in a packed warp, the payoff of a PDE given
+                // as European, whose floor is "never": it marches to the same values again).
+                const bool no_floor = !sc.american;
 #pragma unroll 1
                 for (int c = 0; c < NCH; ++c) {
+                    F fl[8];
+                    tmem::ld8(tbase + T_P + CW * c, fl);
+                    tmem::wait_ld_dep(fl);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int j = pl * NODES + 8 * c + i;
-                        vfin[(8 * c + i) * 32 + lane] = j < xDim ? payoff_node_ni(sc.put, x_node_ni(sc, B.density, j)) : 0.;
+                        double p = (double)fl[i];
+                        if (j >= xDim) p = 0.;
+                        else if (no_floor || j == xDim - 1) p = payoff_node_ni(sc.put, x_node_ni(sc, B.density, j));
+                        vfin[(8 * c + i) * 32 + lane] = p;
                     }
                 }
                 __syncwarp();
