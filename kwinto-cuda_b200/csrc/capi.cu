@@ -206,6 +206,11 @@ const RegVariant g_bs2n2_variant = {158, KW_FD1D_F64, 8, 64, 2, false, false, fd
                                     IwSmem<4>::bytes(), 256, 8};  // 256 < x <= 512: two PDEs per warp
 const RegVariant g_bs2n1_variant = {58, KW_FD1D_F64, 8, 32, 2, false, false, fd1d_iw_kernel<4, 2, true, false, 4>,
                                     IwSmem<4>::bytes(), 256, 16};  // x <= 256: four PDEs per warp
+// the same three with the fp32 march (FD1D.GPU.PRECISION = f32)
+const RegVariant g_bsf_variant[3] = {
+    {1257, KW_FD1D_F32, 8, 128, 2, false, false, fd1d_iw_kernel<4, 2, true, false, 1, float>, IwSmem<4>::bytes(), 256, 4},
+    {1158, KW_FD1D_F32, 8, 64, 2, false, false, fd1d_iw_kernel<4, 2, true, false, 2, float>, IwSmem<4>::bytes(), 256, 8},
+    {1058, KW_FD1D_F32, 8, 32, 2, false, false, fd1d_iw_kernel<4, 2, true, false, 4, float>, IwSmem<4>::bytes(), 256, 16}};
 // 1024 < x <= 2048 / 4096: the wide kernels with BS = true
 const RegVariant g_bs_wide2_variant = {356, KW_FD1D_F64, 8, 256, 2, false, false, nullptr, WideSmem<2>::bytes(), 256, 2, 2,
                                        fd1d_wide_setup_kernel<256>, fd1d_wide_kernel<2, 2, false, true, true>,
@@ -919,7 +924,12 @@ int kw_fd1d_create(const kw_fd1d_config* cfg, kw_fd1d_handle** out)
         const bool wide2 = cfg->x_grid_size > 1024 && cfg->x_grid_size <= 2048;
         const bool wide4 = cfg->x_grid_size > 2048 && cfg->x_grid_size <= 4096;
         const bool seq = cfg->bs_fused == 0 || cfg->bs_fused == 4;  // march as given, then the European copy
-        if (cfg->bs_fused != 1 && cfg->precision == KW_FD1D_F64 && (tile4 || ((tile1 || tile2 || wide2 || wide4) && seq)) &&
+        const bool f32 = cfg->precision == KW_FD1D_F32;
+        if (f32 && cfg->bs_fused != 1 && seq && (tile4 || tile2 || tile1) && cfg->variant == 0) {
+            h->var_bs = &g_bsf_variant[tile4 ? 0 : (tile2 ? 1 : 2)];
+            h->bs_forced = cfg->bs_fused >= 2;
+            if (int rc = prepare_variant(h, h->var_bs, prop, h->ctas_per_sm_bs, h->regs_bs)) return rc;
+        } else if (cfg->bs_fused != 1 && cfg->precision == KW_FD1D_F64 && (tile4 || ((tile1 || tile2 || wide2 || wide4) && seq)) &&
             (cfg->variant == 0 || cfg->bs_fused >= 2)) {
 #ifdef KW_EXPERIMENTS
             h->var_bs = cfg->bs_fused == 2 ? &g_bs1_variant
@@ -1370,6 +1380,7 @@ int kw_fd1d_has_variant(int32_t id, int32_t precision)
 {
     for (int i = 0; i < kNumVariants; ++i)
         if (g_variants[i].id == id && g_variants[i].prec == precision) return 1;
+    if (precision == KW_FD1D_F32 && (id == 1257 || id == 1158 || id == 1058)) return 1;
     if (precision == KW_FD1D_F64 && (id == g_bs2_variant.id || id == g_bs2n2_variant.id || id == g_bs2n1_variant.id || id == g_bs_wide2_variant.id || id == g_bs_wide4_variant.id)) return 1;
 #ifdef KW_EXPERIMENTS
     if (precision == KW_FD1D_F64 && (id == g_bs_variant.id || id == g_bs1_variant.id || id == g_bs253_variant.id)) return 1;

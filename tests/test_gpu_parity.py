@@ -650,6 +650,25 @@ def test_fp32_march_layout_w(x, t, n, variant, oracle):
     assert rel <= 1e-4 and ab <= 5e-5, (x, t, rel, ab)
 
 
+@pytest.mark.parametrize("key,variant", [("bs_1024", 1257), ("bs_700x200", 1257), ("bs_512", 1158), ("bs_300x100", 1158), ("bs_256", 1058), ("bs_200x80", 1058)])
+def test_fp32_fused_bs(key, variant):
+    """FD1D-BS with the fp32 march: fused (one set-up, both marches in fp32, variants 1257 / 1158 / 1058) against the reference's
+    FD1D-BS prices at the fp32 bar and against the two-solve fp32 path."""
+    g = load_golden("bs_fused")
+    t, x = (int(v) for v in g[key + "/grid"])
+    o = g[key + "/options"]
+    p = make_pricer(t, x, mode="FD1D-BS-GPU", **{"FD1D.GPU.PRECISION": "f32", "FD1D.GPU.BS_FUSED": 4})
+    err, got = p.price(o)
+    assert err == "" and p.info()["variant"] == variant, p.info()
+    rel, ab = fp32_error(got, g[key + "/fd1d_bs"])
+    two = make_pricer(t, x, mode="FD1D-BS-GPU", **{"FD1D.GPU.PRECISION": "f32", "FD1D.GPU.BS_FUSED": 1})
+    err, got2 = two.price(o)
+    assert err == "" and two.info()["variant"] not in (1257, 1158, 1058)
+    rel2, ab2 = fp32_error(got2, g[key + "/fd1d_bs"])
+    print("fp32 FD1D-BS", key, "fused rel", rel, "abs", ab, "| two solves rel", rel2, "abs", ab2)
+    assert rel <= 1e-4 and ab <= 5e-5, (key, rel, ab)
+
+
 def test_fp32_march_synthetic_shapes(oracle):
     from kwfd1d.synthetic import synthetic_options
 
