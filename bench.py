@@ -415,8 +415,11 @@ def roofline_of(a, info, n_launch, kernel_ms, local_rank, x=None, t=None):
                            "stale": ent.get("variant") not in (None, info["variant"])}
     except Exception:
         pass
-    if info["variant"] in (237, 137):
-        kname = "fd1d_iw_kernel (Layout W, independent warps)"
+    iw_pack = {237: 1, 137: 1, 239: 1, 138: 2, 38: 4, 1237: 1, 1138: 2, 1038: 4}
+    if info["variant"] in iw_pack:
+        kname = "fd1d_iw_kernel (Layout W, independent warps%s%s)" % (
+            {1: "", 2: ", two PDEs per warp", 4: ", four PDEs per warp"}[iw_pack[info["variant"]]],
+            ", fp32 march" if info["variant"] >= 1000 else "")
     elif info["threads_per_pde"] > 32 and info["variant"] in (331, 336, 431, 436):
         kname = "fd1d_wide_kernel (Layout W, %d warps per PDE)" % (info["threads_per_pde"] // 32)
     elif info["threads_per_pde"] == 32 and (x or a.x) > 256:
