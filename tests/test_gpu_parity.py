@@ -365,6 +365,11 @@ def test_long_chains_are_priced_by_their_own_kernel(x, t, variant, mode):
     err, pb = b.price(o)
     assert err == "" and b.info()["last_n_pde"] == o.shape[0] and b.info()["long_chains"] == 0
     assert np.array_equal(pa, pb), float(np.max(np.abs(pa - pb)))
+    if mode == "FD1D-GPU" and variant == 237:
+        # the same batch through a two-shard handle (both shards on this GPU): every shard has its own long-chain workspace
+        m = make_pricer(t, x, mode=mode, **dict(kw, **{"FD1D.GPU.DEVICES": "0,0"}))
+        err, pm = m.price(o)
+        assert err == "" and m.info()["devices_used"] == 2 and np.array_equal(pm, pa) and m.info()["long_chains"] >= 4, m.info()
     bad = o.copy()
     j = int(np.nonzero((o["t"] == base[3]["t"]) & (o["z"] == base[3]["z"]))[0][7])
     bad["s"][j] = 1e300
